@@ -1,0 +1,452 @@
+#include "engine.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../kernels/kernel_params.h"
+
+// sm_100a cubin embedded by embed_cubin.S (.incbin), the analogue of lib.zig:29-50 @embedFile.
+extern "C" const unsigned char aule_cubin_start[];
+extern "C" const unsigned char aule_cubin_end[];
+
+namespace aule {
+
+using aule_kp::FwdCfg;
+using aule_kp::FwdParams;
+using aule_kp::SimtParams;
+
+static const char* kDtypeSuffix[3] = {"f32", "bf16", "f16"};
+
+CtxGuard::CtxGuard(CudaDriver& drv, CUcontext ctx) : drv_(drv) {
+    CUcontext cur = nullptr;
+    drv_.cuCtxGetCurrent(&cur);
+    if (cur != ctx) {
+        drv_.cuCtxPushCurrent(ctx);
+        pushed_ = true;
+    }
+}
+CtxGuard::~CtxGuard() {
+    if (pushed_) {
+        CUcontext old;
+        drv_.cuCtxPopCurrent(&old);
+    }
+}
+
+std::string Engine::check(CUresult r, const char* what) const {
+    if (r == CUDA_SUCCESS) return "";
+    return std::string(what) + ": " + drv_.error_string(r);
+}
+
+std::string Engine::init() {
+    if (ready_) return "";
+    std::string e = drv_.load();
+    if (!e.empty()) return e;
+    if (!(e = check(drv_.cuInit(0), "cuInit")).empty()) { drv_.unload(); return e; }
+    int n = 0;
+    if (!(e = check(drv_.cuDeviceGetCount(&n), "cuDeviceGetCount")).empty()) { drv_.unload(); return e; }
+    if (n <= 0) { drv_.unload(); return "no CUDA device visible"; }
+    std::string why;
+    for (int i = 0; i < n; ++i) {
+        std::string de = load_device(i);
+        if (!de.empty()) why += (why.empty() ? "" : "; ") + de;
+    }
+    if (devices_.empty()) {
+        drv_.unload();
+        return "no usable sm_100 device: " + why;
+    }
+    ready_ = true;
+    return "";
+}
+
+std::string Engine::load_device(int ordinal) {
+    Device d;
+    d.ordinal = ordinal;
+    std::string e;
+    if (!(e = check(drv_.cuDeviceGet(&d.dev, ordinal), "cuDeviceGet")).empty()) return e;
+    drv_.cuDeviceGetName(d.name, sizeof(d.name), d.dev);
+    drv_.cuDeviceGetAttribute(&d.cc_major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, d.dev);
+    drv_.cuDeviceGetAttribute(&d.cc_minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, d.dev);
+    drv_.cuDeviceGetAttribute(&d.sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, d.dev);
+    if (d.cc_major != 10 || d.cc_minor != 0) {
+        char buf[320];
+        snprintf(buf, sizeof(buf), "device %d (%s) is sm_%d%d; this library carries sm_100a code only", ordinal, d.name,
+                 d.cc_major, d.cc_minor);
+        return buf;
+    }
+    if (!(e = check(drv_.cuDevicePrimaryCtxRetain(&d.ctx, d.dev), "cuDevicePrimaryCtxRetain")).empty()) return e;
+    CtxGuard g(drv_, d.ctx);
+    if (!(e = check(drv_.cuModuleLoadData(&d.mod, aule_cubin_start), "cuModuleLoadData(sm_100a cubin)")).empty()) {
+        drv_.cuDevicePrimaryCtxRelease(d.dev);
+        return e;
+    }
+    auto get = [&](CUfunction* f, const std::string& name) -> std::string {
+        return check(drv_.cuModuleGetFunction(f, d.mod, name.c_str()), name.c_str());
+    };
+    for (int t = 0; t < 3 && e.empty(); ++t) {
+        e = get(&d.fwd_simt[t], std::string("aule_fwd_simt_") + kDtypeSuffix[t]);
+        if (e.empty()) e = get(&d.bwd_dq_simt[t], std::string("aule_bwd_dq_simt_") + kDtypeSuffix[t]);
+        if (e.empty()) e = get(&d.bwd_dkv_simt[t], std::string("aule_bwd_dkv_simt_") + kDtypeSuffix[t]);
+    }
+    for (int t = 1; t < 3 && e.empty(); ++t) {
+        e = get(&d.fwd_sm100[t][0], std::string("aule_fwd_sm100_") + kDtypeSuffix[t] + "_d64");
+        if (e.empty()) e = get(&d.fwd_sm100[t][1], std::string("aule_fwd_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.fwd_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)FwdCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem d64)");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.fwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem d128)");
+    }
+    if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
+    if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_compute, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_out, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    if (!e.empty()) {
+        drv_.cuModuleUnload(d.mod);
+        drv_.cuDevicePrimaryCtxRelease(d.dev);
+        return e;
+    }
+    devices_.push_back(d);
+    return "";
+}
+
+void Engine::shutdown() {
+    if (!ready_) return;
+    for (Device& d : devices_) {
+        CtxGuard g(drv_, d.ctx);
+        drv_.cuCtxSynchronize();
+        for (int i = 0; i < 9; ++i)
+            if (d.stage[i]) drv_.cuMemFree(d.stage[i]);
+        if (d.s_in) drv_.cuStreamDestroy(d.s_in);
+        if (d.s_compute) drv_.cuStreamDestroy(d.s_compute);
+        if (d.s_out) drv_.cuStreamDestroy(d.s_out);
+        if (d.mod) drv_.cuModuleUnload(d.mod);
+    }
+    for (Device& d : devices_) drv_.cuDevicePrimaryCtxRelease(d.dev);
+    devices_.clear();
+    ready_ = false;
+    // The driver library stays loaded (dlclose of libcuda is not safe with live CUDA users
+    // such as PyTorch in the same process).
+}
+
+Device* Engine::by_ordinal(int ordinal) {
+    for (Device& d : devices_)
+        if (d.ordinal == ordinal) return &d;
+    return nullptr;
+}
+
+std::string Engine::validate(const AttnShape& s, int32_t dtype) {
+    char buf[256];
+    if (dtype < 0 || dtype > 2) return "unsupported dtype (0=f32, 1=bf16, 2=f16)";
+    if (!s.B || !s.Hq || !s.Hkv || !s.Sq || !s.Sk || !s.D) return "empty tensor dimension";
+    if (s.Hq % s.Hkv != 0) {   // attention_gpu.zig:383-388, __init__.py:159-160
+        snprintf(buf, sizeof(buf), "heads_q (%u) must be divisible by heads_kv (%u) for GQA", s.Hq, s.Hkv);
+        return buf;
+    }
+    if (s.D > 128 || (s.D % 4) != 0) {   // README.md:202-206 (head_dim <= 128)
+        snprintf(buf, sizeof(buf), "head_dim must be a multiple of 4 and <= 128, got %u", s.D);
+        return buf;
+    }
+    return "";
+}
+
+std::string Engine::launch(Device& d, CUfunction fn, const char* name, unsigned gx, unsigned gy, unsigned gz,
+                           unsigned bx, unsigned smem, CUstream stream, void** params) {
+    std::string e = check(drv_.cuLaunchKernel(fn, gx, gy, gz, bx, 1, 1, smem, stream, params, nullptr), name);
+    if (e.empty()) {
+        ++launches_;
+        last_kernel_ = name;
+    }
+    (void)d;
+    return e;
+}
+
+std::string Engine::make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D) const {
+    // [bh, S, D] 16-bit row-major viewed as a 3-D tensor (D innermost); box = 64 x 128 x 1 with the
+    // 128-byte swizzle the UMMA descriptors in attn_fwd_sm100.cu expect. Out-of-range rows read as 0
+    // and are clipped on store, which is how ragged Sq/Sk tails are handled.
+    cuuint64_t dims[3] = {D, S, bh};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)S * D * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = drv_.cuTensorMapEncodeTiled(
+        m, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims,
+        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return check(r, "cuTensorMapEncodeTiled");
+}
+
+std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                            CUdeviceptr lse, const AttnShape& s, int32_t dtype, float scale, bool causal,
+                            int32_t window) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    std::string e = validate(s, dtype);
+    if (!e.empty()) return e;
+    if (!q || !k || !v || !o) return "null device pointer";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    if (!(scale > 0.f)) scale = 1.0f / sqrtf((float)s.D);   // triton_flash.py:394-395
+    if (window == 0) window = -1;
+
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && window < 0 &&
+                    path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0;
+    if (tc) {
+        CUtensorMap tmQ, tmK, tmV, tmO;
+        if (!(e = make_tmap(&tmQ, dtype, q, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
+        if (!(e = make_tmap(&tmK, dtype, k, (uint64_t)s.B * s.Hkv, s.Sk, s.D)).empty()) return e;
+        if (!(e = make_tmap(&tmV, dtype, v, (uint64_t)s.B * s.Hkv, s.Sk, s.D)).empty()) return e;
+        if (!(e = make_tmap(&tmO, dtype, o, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
+        FwdParams p;
+        p.lse = (float*)lse;
+        p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk;
+        p.num_q_super = (s.Sq + 255) / 256;
+        const uint64_t tiles = (uint64_t)p.num_q_super * s.Hq * s.B;
+        if (tiles > 0xffffffffull) return "problem too large (work-item count exceeds 2^32)";
+        p.num_tiles = (uint32_t)tiles;
+        p.scale = scale;
+        p.scale_log2 = scale * 1.4426950408889634f;
+        p.causal = causal ? 1 : 0;
+        const bool d128 = s.D == 128;
+        const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
+        const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)d.sm_count);
+        void* params[] = {&tmQ, &tmK, &tmV, &tmO, &p};
+        char name[64];
+        snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+        return launch(d, d.fwd_sm100[dtype][d128 ? 1 : 0], name, grid, 1, 1, 512, smem, stream, params);
+    }
+    SimtParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = (const void*)q; p.k = (const void*)k; p.v = (const void*)v; p.o = (void*)o;
+    p.lse = (float*)lse;
+    p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk; p.D = s.D;
+    p.scale = scale; p.causal = causal ? 1 : 0; p.window = window;
+    if (s.Hq > 65535 || s.B > 65535) return "heads/batch exceed the CUDA grid limit (65535)";
+    void* params[] = {&p};
+    char name[64];
+    snprintf(name, sizeof(name), "aule_fwd_simt_%s", kDtypeSuffix[dtype]);
+    return launch(d, d.fwd_simt[dtype], name, (s.Sq + aule_kp::SIMT_ROWS - 1) / aule_kp::SIMT_ROWS, s.Hq, s.B,
+                  aule_kp::SIMT_ROWS * aule_kp::SIMT_LANES, 0, stream, params);
+}
+
+std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                             CUdeviceptr d_o, CUdeviceptr lse, CUdeviceptr dq, CUdeviceptr dk, CUdeviceptr dv,
+                             const AttnShape& s, int32_t dtype, float scale, bool causal) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    std::string e = validate(s, dtype);
+    if (!e.empty()) return e;
+    if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv) return "null device pointer";
+    if (s.Hq > 65535 || s.B > 65535) return "heads/batch exceed the CUDA grid limit (65535)";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    if (!(scale > 0.f)) scale = 1.0f / sqrtf((float)s.D);
+    CUdeviceptr delta = 0;
+    const size_t dbytes = (size_t)s.B * s.Hq * s.Sq * sizeof(float);
+    if (!(e = check(drv_.cuMemAllocAsync(&delta, dbytes, stream), "cuMemAllocAsync(delta)")).empty()) return e;
+    SimtParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = (const void*)q; p.k = (const void*)k; p.v = (const void*)v; p.o = (void*)o;
+    p.lse = (float*)lse; p.d_o = (const void*)d_o;
+    p.dq = (void*)dq; p.dk = (void*)dk; p.dv = (void*)dv; p.delta = (float*)delta;
+    p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk; p.D = s.D;
+    p.scale = scale; p.causal = causal ? 1 : 0; p.window = -1;
+    void* params[] = {&p};
+    char name[64];
+    const unsigned threads = aule_kp::SIMT_ROWS * aule_kp::SIMT_LANES;
+    snprintf(name, sizeof(name), "aule_bwd_dq_simt_%s", kDtypeSuffix[dtype]);
+    e = launch(d, d.bwd_dq_simt[dtype], name, (s.Sq + aule_kp::SIMT_ROWS - 1) / aule_kp::SIMT_ROWS, s.Hq, s.B, threads,
+               0, stream, params);
+    if (e.empty()) {
+        snprintf(name, sizeof(name), "aule_bwd_dkv_simt_%s", kDtypeSuffix[dtype]);
+        e = launch(d, d.bwd_dkv_simt[dtype], name, (s.Sk + aule_kp::SIMT_ROWS - 1) / aule_kp::SIMT_ROWS, s.Hkv, s.B,
+                   threads, 0, stream, params);
+    }
+    drv_.cuMemFreeAsync(delta, stream);
+    return e;
+}
+
+std::string Engine::ensure_stage(Device& d, int slot, size_t bytes) {
+    if (d.stage_cap[slot] >= bytes) return "";
+    if (d.stage[slot]) {
+        drv_.cuCtxSynchronize();
+        drv_.cuMemFree(d.stage[slot]);
+        d.stage[slot] = 0;
+        d.stage_cap[slot] = 0;
+    }
+    std::string e = check(drv_.cuMemAlloc(&d.stage[slot], bytes), "cuMemAlloc(staging)");
+    if (e.empty()) d.stage_cap[slot] = bytes;
+    return e;
+}
+
+std::string Engine::forward_host(int dev, const void* q, const void* k, const void* v, void* o, float* lse,
+                                 const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window,
+                                 int* stage_code) {
+    *stage_code = -1;
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    *stage_code = -4;
+    std::string e = validate(s, dtype);
+    if (!e.empty()) return e;
+    if (!q || !k || !v || !o) return "null host pointer";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    const size_t es = dtype_size(dtype);
+    const uint32_t group = s.Hq / s.Hkv;
+    const size_t q_unit = (size_t)group * s.Sq * s.D * es;      // bytes of Q/O per (batch, kv-head) unit
+    const size_t kv_unit = (size_t)s.Sk * s.D * es;
+    const size_t lse_unit = (size_t)group * s.Sq * sizeof(float);
+    const uint32_t units = s.B * s.Hkv;
+    *stage_code = -2;
+    if (!(e = ensure_stage(d, 0, q_unit * units)).empty()) return e;
+    if (!(e = ensure_stage(d, 1, kv_unit * units)).empty()) return e;
+    if (!(e = ensure_stage(d, 2, kv_unit * units)).empty()) return e;
+    if (!(e = ensure_stage(d, 3, q_unit * units)).empty()) return e;
+    if (lse && !(e = ensure_stage(d, 4, lse_unit * units)).empty()) return e;
+
+    // Chunk over units so that copy-in of chunk c+1, the kernel of chunk c and copy-out of
+    // chunk c-1 overlap (three streams, events between them).
+    const uint32_t nchunks = std::min<uint32_t>(units, 8);
+    const uint32_t per = (units + nchunks - 1) / nchunks;
+    std::vector<CUevent> ev_in(nchunks, nullptr), ev_c(nchunks, nullptr);
+    auto cleanup = [&]() {
+        for (CUevent x : ev_in) if (x) drv_.cuEventDestroy(x);
+        for (CUevent x : ev_c) if (x) drv_.cuEventDestroy(x);
+    };
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        drv_.cuEventCreate(&ev_in[c], CU_EVENT_DISABLE_TIMING);
+        drv_.cuEventCreate(&ev_c[c], CU_EVENT_DISABLE_TIMING);
+    }
+    int code = 0;
+    for (uint32_t c = 0; c < nchunks && e.empty(); ++c) {
+        const uint32_t u0 = c * per;
+        if (u0 >= units) break;
+        const uint32_t nu = std::min(per, units - u0);
+        code = -3;
+        e = check(drv_.cuMemcpyHtoDAsync(d.stage[0] + u0 * q_unit, (const char*)q + u0 * q_unit, nu * q_unit, d.s_in), "upload Q");
+        if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[1] + u0 * kv_unit, (const char*)k + u0 * kv_unit, nu * kv_unit, d.s_in), "upload K");
+        if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[2] + u0 * kv_unit, (const char*)v + u0 * kv_unit, nu * kv_unit, d.s_in), "upload V");
+        if (e.empty()) e = check(drv_.cuEventRecord(ev_in[c], d.s_in), "cuEventRecord");
+        if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_compute, ev_in[c], 0), "cuStreamWaitEvent");
+        if (!e.empty()) break;
+        code = -4;
+        // A chunk of `nu` units is itself a [nu, group, S, D] / [nu, 1, S, D] attention problem.
+        AttnShape cs{nu, group, 1, s.Sq, s.Sk, s.D};
+        e = forward(dev, d.s_compute, d.stage[0] + u0 * q_unit, d.stage[1] + u0 * kv_unit, d.stage[2] + u0 * kv_unit,
+                    d.stage[3] + u0 * q_unit, lse ? d.stage[4] + u0 * lse_unit : 0, cs, dtype, scale, causal, window);
+        if (e.empty()) e = check(drv_.cuEventRecord(ev_c[c], d.s_compute), "cuEventRecord");
+        if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_out, ev_c[c], 0), "cuStreamWaitEvent");
+        if (!e.empty()) break;
+        code = -5;
+        e = check(drv_.cuMemcpyDtoHAsync((char*)o + u0 * q_unit, d.stage[3] + u0 * q_unit, nu * q_unit, d.s_out), "download O");
+        if (e.empty() && lse)
+            e = check(drv_.cuMemcpyDtoHAsync((char*)lse + u0 * lse_unit, d.stage[4] + u0 * lse_unit, nu * lse_unit, d.s_out), "download LSE");
+    }
+    if (e.empty()) { code = -4; e = check(drv_.cuStreamSynchronize(d.s_compute), "attention kernel"); }
+    if (e.empty()) { code = -5; e = check(drv_.cuStreamSynchronize(d.s_out), "download"); }
+    if (!e.empty()) { drv_.cuStreamSynchronize(d.s_in); drv_.cuStreamSynchronize(d.s_compute); drv_.cuStreamSynchronize(d.s_out); }
+    cleanup();
+    *stage_code = e.empty() ? 0 : code;
+    return e;
+}
+
+std::string Engine::backward_host(int dev, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                  const float* lse, void* dq, void* dk, void* dv, const AttnShape& s, int32_t dtype,
+                                  float scale, bool causal, int* stage_code) {
+    *stage_code = -1;
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    *stage_code = -4;
+    std::string e = validate(s, dtype);
+    if (!e.empty()) return e;
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    const size_t es = dtype_size(dtype);
+    const size_t qb = (size_t)s.B * s.Hq * s.Sq * s.D * es, kb = (size_t)s.B * s.Hkv * s.Sk * s.D * es;
+    const size_t lb = (size_t)s.B * s.Hq * s.Sq * sizeof(float);
+    const size_t sizes[9] = {qb, kb, kb, qb, lb, qb, qb, kb, kb};   // q k v o lse do dq dk dv
+    *stage_code = -2;
+    for (int i = 0; i < 9; ++i)
+        if (!(e = ensure_stage(d, i, sizes[i])).empty()) return e;
+    *stage_code = -3;
+    const void* src[6] = {q, k, v, o, lse, d_o};
+    for (int i = 0; i < 6; ++i)
+        if (!(e = check(drv_.cuMemcpyHtoDAsync(d.stage[i], src[i], sizes[i], d.s_compute), "upload")).empty()) return e;
+    *stage_code = -4;
+    e = backward(dev, d.s_compute, d.stage[0], d.stage[1], d.stage[2], d.stage[3], d.stage[5], d.stage[4], d.stage[6],
+                 d.stage[7], d.stage[8], s, dtype, scale, causal);
+    if (!e.empty()) return e;
+    void* dst[3] = {dq, dk, dv};
+    for (int i = 0; i < 3; ++i)
+        if (!(e = check(drv_.cuMemcpyDtoHAsync(dst[i], d.stage[6 + i], sizes[6 + i], d.s_compute), "download")).empty()) {
+            *stage_code = -5;
+            return e;
+        }
+    if (!(e = check(drv_.cuStreamSynchronize(d.s_compute), "backward kernels")).empty()) return e;
+    *stage_code = 0;
+    return "";
+}
+
+std::string Engine::smoke_multiply(int dev, const float* in, float* out, uint32_t n) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    std::string e;
+    if (!(e = ensure_stage(d, 0, (size_t)n * 4)).empty()) return e;
+    if (!(e = ensure_stage(d, 3, (size_t)n * 4)).empty()) return e;
+    if (!(e = check(drv_.cuMemcpyHtoDAsync(d.stage[0], in, (size_t)n * 4, d.s_compute), "upload")).empty()) return e;
+    CUdeviceptr a = d.stage[0], b = d.stage[3];
+    void* params[] = {&a, &b, &n};
+    if (!(e = launch(d, d.smoke, "aule_smoke_multiply", (n + 255) / 256, 1, 1, 256, 0, d.s_compute, params)).empty()) return e;
+    if (!(e = check(drv_.cuMemcpyDtoHAsync(out, b, (size_t)n * 4, d.s_compute), "download")).empty()) return e;
+    return check(drv_.cuStreamSynchronize(d.s_compute), "smoke kernel");
+}
+
+std::string Engine::mem_alloc(int dev, size_t bytes, CUdeviceptr* out) {
+    if (!ready_) return "Not initialized";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    return check(drv_.cuMemAlloc(out, bytes ? bytes : 4), "cuMemAlloc");
+}
+void Engine::mem_free(int dev, CUdeviceptr p) {
+    Device* dp = ready_ ? by_ordinal(dev) : nullptr;
+    if (!dp || !p) return;
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    drv_.cuMemFree(p);
+}
+std::string Engine::copy_h2d(int dev, CUdeviceptr dst, const void* src, size_t bytes) {
+    Device* dp = ready_ ? by_ordinal(dev) : nullptr;
+    if (!dp) return "invalid device index";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    return check(drv_.cuMemcpyHtoD(dst, src, bytes), "cuMemcpyHtoD");
+}
+std::string Engine::copy_d2h(int dev, void* dst, CUdeviceptr src, size_t bytes) {
+    Device* dp = ready_ ? by_ordinal(dev) : nullptr;
+    if (!dp) return "invalid device index";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    return check(drv_.cuMemcpyDtoH(dst, src, bytes), "cuMemcpyDtoH");
+}
+std::string Engine::synchronize(int dev) {
+    if (!ready_) return "Not initialized";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    return check(drv_.cuCtxSynchronize(), "cuCtxSynchronize");
+}
+
+}  // namespace aule

@@ -1,0 +1,123 @@
+// Attention engine over the CUDA Driver API: per-device primary context, the embedded
+// sm_100a module, TMA descriptor construction and kernel launches.
+//
+// Role-for-role replacement of the reference's device runtime and pipelines:
+//   Engine::init / Device            <- src/vulkan_context.zig:52-251 (instance/device/queue),
+//                                       src/backends/hip.zig:133-160 (module load)
+//   Engine::forward / backward       <- src/attention_gpu.zig:360-453,:707-830 (AttentionEngine),
+//                                       src/attention_pipeline.zig:312-391 (dispatch),
+//                                       src/attention_backward_pipeline.zig:228-257,:490-519
+//   DeviceBuffer / staging           <- src/buffer_manager.zig:39-78, src/gpu_tensor.zig:32-94
+//   Engine::smoke_multiply           <- src/compute_pipeline.zig:203-254 + shaders/test.comp
+// Unlike the reference (one blocking vkQueueSubmit + fence per call,
+// attention_pipeline.zig:377-390) the device-pointer entry points are asynchronous on the
+// caller's stream.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "cuda_driver.h"
+
+namespace aule {
+
+enum DType : int32_t { kF32 = 0, kBF16 = 1, kF16 = 2 };
+inline size_t dtype_size(int32_t dt) { return dt == kF32 ? 4 : 2; }
+
+struct AttnShape {
+    uint32_t B, Hq, Hkv, Sq, Sk, D;
+};
+
+enum KernelPath : int32_t { kAuto = 0, kForceCudaCore = 1 };
+
+struct Device {
+    int ordinal = -1;
+    CUdevice dev = 0;
+    CUcontext ctx = nullptr;
+    CUmodule mod = nullptr;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    char name[256] = {0};
+    // kernels
+    CUfunction fwd_simt[3] = {nullptr, nullptr, nullptr};      // indexed by DType
+    CUfunction bwd_dq_simt[3] = {nullptr, nullptr, nullptr};
+    CUfunction bwd_dkv_simt[3] = {nullptr, nullptr, nullptr};
+    CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
+    CUfunction smoke = nullptr;
+    // streams for the host-staged entry points
+    CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    // grow-only staging buffers for host-pointer calls: q k v o lse do dq dk dv
+    CUdeviceptr stage[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    size_t stage_cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+class Engine {
+public:
+    // "" on success. Idempotent.
+    std::string init();
+    void shutdown();
+    bool ready() const { return ready_; }
+    int device_count() const { return (int)devices_.size(); }
+    // Devices are addressed by CUDA ordinal everywhere (== torch device index).
+    Device* by_ordinal(int ordinal);
+    const Device* first() const { return devices_.empty() ? nullptr : &devices_[0]; }
+    CudaDriver& driver() { return drv_; }
+
+    // Validation shared by every entry (mirrors attention_gpu.zig:372-404 widened to GQA,
+    // D <= 128, Sq != Sk). Returns "" or the reason.
+    static std::string validate(const AttnShape& s, int32_t dtype);
+
+    // Asynchronous on `stream` of device `dev`. Device pointers. Returns "" or an error.
+    std::string forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                        CUdeviceptr lse, const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window);
+    std::string backward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                         CUdeviceptr d_o, CUdeviceptr lse, CUdeviceptr dq, CUdeviceptr dk, CUdeviceptr dv,
+                         const AttnShape& s, int32_t dtype, float scale, bool causal);
+    // Synchronous, host pointers, chunked + pipelined over (batch x kv-head) units.
+    // `stage_code` receives the reference's failure stage (-2 alloc, -3 upload, -4 compute, -5 download).
+    std::string forward_host(int dev, const void* q, const void* k, const void* v, void* o, float* lse,
+                             const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window,
+                             int* stage_code);
+    std::string backward_host(int dev, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                              const float* lse, void* dq, void* dk, void* dv, const AttnShape& s, int32_t dtype,
+                              float scale, bool causal, int* stage_code);
+    std::string smoke_multiply(int dev, const float* in, float* out, uint32_t n);
+
+    // Raw memory for the handle-table tensors (device 0).
+    std::string mem_alloc(int dev, size_t bytes, CUdeviceptr* out);
+    void mem_free(int dev, CUdeviceptr p);
+    std::string copy_h2d(int dev, CUdeviceptr dst, const void* src, size_t bytes);
+    std::string copy_d2h(int dev, void* dst, CUdeviceptr src, size_t bytes);
+    std::string synchronize(int dev);
+
+    void set_kernel_path(int32_t p) { path_ = p; }
+    uint64_t launch_count() const { return launches_; }
+    const char* last_kernel() const { return last_kernel_.c_str(); }
+
+private:
+    std::string check(CUresult r, const char* what) const;
+    std::string load_device(int ordinal);
+    std::string ensure_stage(Device& d, int slot, size_t bytes);
+    std::string launch(Device& d, CUfunction fn, const char* name, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
+                       unsigned smem, CUstream stream, void** params);
+    std::string make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D) const;
+
+    CudaDriver drv_;
+    std::vector<Device> devices_;
+    bool ready_ = false;
+    int32_t path_ = kAuto;
+    uint64_t launches_ = 0;
+    std::string last_kernel_ = "none";
+};
+
+// RAII: make a device's primary context current for the duration of a call.
+class CtxGuard {
+public:
+    CtxGuard(CudaDriver& drv, CUcontext ctx);
+    ~CtxGuard();
+private:
+    CudaDriver& drv_;
+    bool pushed_ = false;
+};
+
+}  // namespace aule

@@ -1,0 +1,51 @@
+// Kernel parameter blocks and shared-memory layouts shared by the device code
+// (csrc/kernels/*.cu) and the host launcher (csrc/host/engine.cpp).  Plain structs only.
+#pragma once
+#include <stdint.h>
+
+namespace aule_kp {
+
+// ---- CUDA-core kernels (attn_simt.cu) -------------------------------------------------
+struct SimtParams {
+    const void* q; const void* k; const void* v; void* o;
+    float* lse;                  // [B,Hq,Sq] or nullptr (forward) / required (backward)
+    const void* d_o; void* dq; void* dk; void* dv;
+    float* delta;                // [B,Hq,Sq] workspace (backward)
+    uint32_t B, Hq, Hkv, Sq, Sk, D;
+    float scale;
+    int32_t causal, window;
+};
+constexpr int SIMT_ROWS = 32, SIMT_LANES = 8;
+
+// ---- tcgen05 forward (attn_fwd_sm100.cu) ----------------------------------------------
+struct FwdParams {
+    float* lse;               // [B,Hq,Sq] fp32 or nullptr
+    uint32_t B, Hq, Hkv, Sq, Sk;
+    uint32_t num_q_super;     // ceil(Sq / 256)
+    uint32_t num_tiles;       // num_q_super * Hq * B
+    float scale;              // softmax scale (natural)
+    float scale_log2;         // scale * log2(e)
+    int32_t causal;
+};
+
+template <int D>
+struct FwdCfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
+    static constexpr int NS = (D == 128) ? 3 : 6;               // K/V ring stages
+    static constexpr int CHUNKS = D / 64;                       // 128-byte swizzle chunks per row
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;          // [128 rows][128 B]
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_Q = 0;
+    static constexpr uint32_t OFF_KV = OFF_Q + 2 * TILE_BYTES;
+    static constexpr uint32_t OFF_O = OFF_KV + NS * TILE_BYTES;
+    static constexpr uint32_t OFF_STAT = OFF_O + 2 * TILE_BYTES;   // float l[2][128], m[2][128]
+    static constexpr uint32_t OFF_BAR = OFF_STAT + 4 * 128 * 4;
+    static constexpr int NBAR = 16 + 2 * NS;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+    // TMEM columns
+    static constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 256 + D;
+};
+
+
+}  // namespace aule_kp

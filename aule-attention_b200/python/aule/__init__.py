@@ -1,0 +1,227 @@
+"""
+aule (B200 build): FlashAttention-2 on NVIDIA B200 behind the aule-attention API.
+
+Same public surface as the reference package (/root/reference/python/aule/__init__.py:564-592):
+
+    from aule import flash_attention
+    out = flash_attention(q, k, v, causal=True)          # [B, H, S, D] tensors
+
+but ONE backend: hand-written sm_100a CUDA kernels in libaule.so, driven through a C ABI
+(include/aule.h).  torch CUDA tensors cross the boundary as raw device pointers on the
+current stream; NumPy arrays / host tensors go through the pipelined host-buffer entry.
+There is no Triton, no Vulkan, no multi-backend dispatch and no CPU fallback: without a
+B200 every compute call raises.
+"""
+import logging
+import warnings
+
+__version__ = "0.5.0"            # API level of the reference this build is a drop-in for (__init__.py:26)
+__author__ = "Aule Technologies (B200 engine: aule-attention_b200)"
+
+logger = logging.getLogger(__name__)
+
+_backend_errors = {}
+_cuda_available = False
+
+from .ffi import Aule, GpuTensor, AuleError  # noqa: E402  (same names the reference exports, __init__.py:91)
+from . import ffi as _ffi  # noqa: E402
+
+try:
+    _ffi.ensure_init()
+    _cuda_available = True
+    logger.debug("CUDA sm_100 backend loaded successfully")
+except Exception as e:  # library missing or no B200: recorded, reported, never papered over
+    _backend_errors['cuda'] = str(e)
+    logger.debug(f"CUDA sm_100 backend failed to load: {e}")
+
+_original_sdpa = None
+_installed = False
+_forced_backend = None    # kept for signature parity; only None / 'cuda' are accepted
+_verbose = False
+
+
+def _validate(query, key, value):
+    """Shape checks of the reference entry point (__init__.py:140-160), same messages."""
+    if query.ndim != 4:
+        raise ValueError(f"query must be 4D [batch, heads, seq_len, head_dim], got shape {query.shape}")
+    if key.ndim != 4:
+        raise ValueError(f"key must be 4D [batch, heads, seq_len, head_dim], got shape {key.shape}")
+    if value.ndim != 4:
+        raise ValueError(f"value must be 4D [batch, heads, seq_len, head_dim], got shape {value.shape}")
+    batch_q, heads_q, seq_q, head_dim_q = query.shape
+    batch_k, heads_kv, seq_k, head_dim_k = key.shape
+    batch_v, heads_v, seq_v, head_dim_v = value.shape
+    if batch_q != batch_k or batch_q != batch_v:
+        raise ValueError(f"Batch size mismatch: query={batch_q}, key={batch_k}, value={batch_v}")
+    if head_dim_q != head_dim_k or head_dim_q != head_dim_v:
+        raise ValueError(f"head_dim mismatch: query={head_dim_q}, key={head_dim_k}, value={head_dim_v}")
+    if seq_k != seq_v:
+        raise ValueError(f"Key/value seq_len mismatch: key={seq_k}, value={seq_v}")
+    if heads_kv != heads_v:
+        raise ValueError(f"Key/value heads mismatch: key={heads_kv}, value={heads_v}")
+    if heads_q % heads_kv != 0:
+        raise ValueError(f"heads_q ({heads_q}) must be divisible by heads_kv ({heads_kv}) for GQA")
+    if head_dim_q > 128 or head_dim_q % 4 != 0:
+        raise ValueError(f"head_dim must be a multiple of 4 and <= 128, got {head_dim_q}")
+
+
+def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, scale=None, window_size=-1):
+    """
+    FlashAttention-2 forward (differentiable for torch CUDA tensors).
+
+    Signature and argument meaning of the reference (__init__.py:104-129).
+
+    Args:
+        query: [batch, heads_q, seq_len_q, head_dim] - torch.Tensor or numpy.ndarray
+        key:   [batch, heads_kv, seq_len_k, head_dim]
+        value: [batch, heads_kv, seq_len_k, head_dim]
+        rot_cos / rot_sin: accepted for signature parity; like the reference's GPU path
+            (__init__.py:204-207 does not forward them) they are not applied -- a warning is issued.
+        causal: top-left aligned causal mask (default True)
+        scale: softmax scale (default 1/sqrt(head_dim))
+        window_size: sliding window (-1 = full attention)
+
+    Returns: tensor with the shape (and dtype/device kind) of `query`.
+    Raises: ValueError for invalid shapes; RuntimeError if no B200 backend is available.
+    """
+    _validate(query, key, value)
+    if not _cuda_available:
+        raise RuntimeError("aule (B200 build): CUDA sm_100 backend not available and there is no CPU fallback: "
+                           + _backend_errors.get('cuda', 'unknown error'))
+    if rot_cos is not None or rot_sin is not None:
+        warnings.warn("rot_cos/rot_sin are not applied by flash_attention on the CUDA path "
+                      "(same as the reference's GPU path); apply RoPE before calling", stacklevel=2)
+    if _verbose:
+        print(f"aule-attention: cuda-sm100 | shape={tuple(query.shape)} | causal={causal}")
+
+    is_torch = False
+    try:
+        import torch
+        is_torch = isinstance(query, torch.Tensor)
+    except ImportError:
+        pass
+
+    if is_torch:
+        from . import cuda_flash
+        if query.is_cuda:
+            return cuda_flash.flash_attention_cuda(query, key, value, causal=causal, scale=scale, window_size=window_size)
+        # host tensors: staged through HBM by the library (still GPU compute, not a CPU fallback)
+        out = cuda_flash.flash_attention_host(query, key, value, causal=causal, scale=scale, window_size=window_size)
+        return out.to(query.dtype)
+
+    import numpy as np
+    q = np.ascontiguousarray(query, dtype=np.float32)
+    k = np.ascontiguousarray(key, dtype=np.float32)
+    v = np.ascontiguousarray(value, dtype=np.float32)
+    out = np.empty_like(q)
+    lib = _ffi.ensure_init()
+    B, Hq, Sq, D = q.shape
+    _, Hkv, Sk, _ = k.shape
+    rc = lib.aule_attention_forward_host(q.ctypes.data, k.ctypes.data, v.ctypes.data, out.ctypes.data, None,
+                                         B, Hq, Hkv, Sq, Sk, D, _ffi.DTYPE_F32, float(scale) if scale else 0.0,
+                                         1 if causal else 0, int(window_size), 0)
+    if rc != 0:
+        raise AuleError(f"Attention failed: {_ffi.last_error()}")
+    return out.astype(query.dtype, copy=False)
+
+
+attention = flash_attention      # alias, __init__.py:275
+
+
+# =============================================================================
+# PyTorch SDPA compatibility layer (reference __init__.py:288-442)
+# =============================================================================
+def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None,
+                                 enable_gqa=False):
+    """Drop-in for torch.nn.functional.scaled_dot_product_attention. Falls back to the original
+    SDPA for features outside the kernel (mask / dropout), same rule as __init__.py:321-347."""
+    import torch
+    needs_fallback = (attn_mask is not None or dropout_p > 0.0 or not _cuda_available or not query.is_cuda
+                      or query.dim() != 4 or query.shape[-1] > 128 or query.shape[-1] % 4 != 0
+                      or (is_causal and query.shape[-2] != key.shape[-2])      # SDPA's causal is top-left too, but be strict
+                      or (query.shape[1] != key.shape[1] and not enable_gqa))
+    if needs_fallback:
+        fn = _original_sdpa if _original_sdpa is not None else torch.nn.functional.scaled_dot_product_attention
+        if fn is scaled_dot_product_attention:
+            raise RuntimeError("no original SDPA available for fallback")
+        return fn(query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale,
+                  enable_gqa=enable_gqa)
+    return flash_attention(query, key, value, causal=is_causal, scale=scale)
+
+
+def install(backend=None, verbose=False):
+    """Install as torch's SDPA (reference __init__.py:353-421). `backend` accepts None or 'cuda'."""
+    global _original_sdpa, _installed, _forced_backend, _verbose
+    import torch
+    import torch.nn.functional as F
+    if backend is not None and backend != 'cuda':
+        raise ValueError(f"Invalid backend '{backend}'. This build has a single backend: 'cuda' (or None)")
+    if _installed:
+        _forced_backend, _verbose = backend, verbose
+        print(f"aule-attention: Updated (backend={backend or 'auto'}, verbose={verbose})")
+        return
+    _original_sdpa = F.scaled_dot_product_attention
+    F.scaled_dot_product_attention = scaled_dot_product_attention
+    torch.nn.functional.scaled_dot_product_attention = scaled_dot_product_attention
+    _installed, _forced_backend, _verbose = True, backend, verbose
+    print(f"aule-attention: Installed (cuda-sm100{', verbose' if verbose else ''})")
+
+
+def uninstall():
+    """Restore the original SDPA (reference __init__.py:424-442)."""
+    global _installed
+    if not _installed:
+        print("aule-attention: Not installed")
+        return
+    import torch
+    import torch.nn.functional as F
+    if _original_sdpa is not None:
+        F.scaled_dot_product_attention = _original_sdpa
+        torch.nn.functional.scaled_dot_product_attention = _original_sdpa
+    _installed = False
+    print("aule-attention: Uninstalled, restored PyTorch SDPA")
+
+
+# =============================================================================
+# Backend introspection (reference __init__.py:445-561)
+# =============================================================================
+def get_available_backends():
+    return ['cuda'] if _cuda_available else []
+
+
+def get_backend_errors():
+    return dict(_backend_errors)
+
+
+def get_backend_info():
+    info = {}
+    if _cuda_available:
+        try:
+            dev = Aule().get_device_info()
+            info['cuda'] = {'available': True, 'device': dev.get('device_name', 'Unknown'),
+                            'sm_count': dev.get('sm_count'), 'devices': dev.get('devices'),
+                            'description': 'sm_100a tcgen05/TMA FlashAttention-2 (libaule.so)'}
+        except Exception:
+            info['cuda'] = {'available': True, 'device': 'Unknown'}
+    else:
+        info['cuda'] = {'available': False, 'error': _backend_errors.get('cuda')}
+    return info
+
+
+def print_backend_info():
+    print("=" * 60)
+    print("AULE-ATTENTION (B200 build) v" + __version__)
+    print("=" * 60)
+    print(f"Available backends: {get_available_backends()}")
+    for name, d in get_backend_info().items():
+        print(f"[{name.upper()}] {d}")
+    print("=" * 60)
+
+
+__all__ = [
+    "flash_attention", "attention", "scaled_dot_product_attention",
+    "install", "uninstall",
+    "get_available_backends", "get_backend_errors", "get_backend_info", "print_backend_info",
+    "Aule", "GpuTensor", "AuleError",
+    "__version__",
+]

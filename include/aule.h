@@ -1,0 +1,187 @@
+/*
+ * libaule C ABI  --  the drop-in boundary of the B200-native attention engine.
+ *
+ * Part 1 re-declares, symbol for symbol, the C ABI the reference exports from
+ * src/lib.zig (so /root/reference/python/aule/vulkan.py loads this library
+ * unmodified through ctypes.CDLL, vulkan.py:205-207,:224-406).  Each entry
+ * cites the reference export it replaces.
+ *
+ * Part 2 is the extension the reference does not have and BASELINE.json's
+ * north_star requires: raw device pointers (PyTorch tensor.data_ptr()),
+ * bf16/fp16, explicit scale, GQA, D=128, a caller-supplied CUstream, and a
+ * pipelined host-buffer entry used for end-to-end measurements.
+ *
+ * Conventions (same as the reference, lib.zig:12-26,:124-130):
+ *   - all tensors are contiguous row-major [B, H, S, D];
+ *   - 0 = success, negative = failure, message via aule_get_error();
+ *   - global state, single-threaded by contract;
+ *   - no CPU fallback: every compute entry fails with an error when no
+ *     sm_100 device / CUDA driver is present.
+ */
+#ifndef AULE_H_
+#define AULE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AULE_API __declspec(dllexport)
+#else
+#define AULE_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Part 1: the reference's ABI (src/lib.zig)                                 */
+/* ------------------------------------------------------------------------ */
+
+/* lib.zig:59-93   0 ok / -1 fail; idempotent. Opens the CUDA driver (dlopen
+ * libcuda.so.1), retains the primary context of every visible sm_100 device,
+ * loads the embedded sm_100a cubin (cuModuleLoadData). */
+AULE_API int32_t aule_init(void);
+/* lib.zig:105-122  destroys all handle-table tensors, then the contexts. */
+AULE_API void aule_shutdown(void);
+/* lib.zig:124-130  static 512-byte buffer; "No error" if none. */
+AULE_API const char* aule_get_error(void);
+/* lib.zig:133-141 */
+AULE_API const char* aule_get_backend_name(void);
+/* lib.zig:96-103   1 when the backward kernels are available. */
+AULE_API int32_t aule_supports_backward(void);
+/* lib.zig:144-163 / :274-293   0 other,1 amd,2 nvidia,3 intel,4 apple,-1 not init */
+AULE_API int32_t aule_get_vendor(void);
+AULE_API int32_t aule_get_gpu_vendor(void);
+/* lib.zig:242-271  bytes written or -1 */
+AULE_API int32_t aule_get_device_name(char* buffer, uint32_t buffer_len);
+/* lib.zig:168-197,:296-309 */
+AULE_API int32_t aule_is_amd_optimized(void);
+AULE_API int32_t aule_has_fp16(void);
+AULE_API int32_t aule_get_subgroup_size(void);
+/* lib.zig:202-239  single "sm100" variant: id 0 accepted, others -2 */
+AULE_API int32_t aule_set_shader_variant(uint8_t variant);
+AULE_API int32_t aule_get_shader_variant(void);
+AULE_API int32_t aule_has_shader_variant(uint8_t variant);
+
+/* lib.zig:312-367  host fp32 pointers, MHA, Sq == Sk, scale = 1/sqrt(D).
+ * codes: -1 not-init, -2 alloc, -3 upload, -4 compute, -5 download */
+AULE_API int32_t aule_attention_forward(const float* query, const float* key, const float* value,
+                                        float* output, uint32_t batch_size, uint32_t num_heads,
+                                        uint32_t seq_len, uint32_t head_dim, int32_t causal);
+/* lib.zig:765-852  also writes LSE [B,H,S] (natural log, scaled scores) */
+AULE_API int32_t aule_attention_forward_with_lse(const float* query, const float* key,
+                                                 const float* value, float* output, float* lse_out,
+                                                 uint32_t batch_size, uint32_t num_heads,
+                                                 uint32_t seq_len, uint32_t head_dim, int32_t causal);
+/* lib.zig:639-762 */
+AULE_API int32_t aule_attention_backward(const float* query, const float* key, const float* value,
+                                         const float* output, const float* grad_output,
+                                         const float* lse, float* grad_query, float* grad_key,
+                                         float* grad_value, uint32_t batch_size, uint32_t num_heads,
+                                         uint32_t seq_len, uint32_t head_dim, int32_t causal);
+
+/* lib.zig:409-455  u64 handle = slot+1, 0 = failure; at most 1024 live (:17).
+ * Tensors are TRUE device memory here (the reference uses host-visible
+ * memory, gpu_tensor.zig:50). Element type is 32-bit (f32 / u32). */
+AULE_API uint64_t aule_tensor_create(uint32_t batch_size, uint32_t num_heads, uint32_t seq_len,
+                                     uint32_t head_dim);
+AULE_API uint64_t aule_tensor_create_u32(uint32_t batch_size, uint32_t num_heads, uint32_t seq_len,
+                                         uint32_t head_dim);
+AULE_API void aule_tensor_destroy(uint64_t handle);
+/* lib.zig:457-494  -1 bad handle / not init, -3 size mismatch */
+AULE_API int32_t aule_tensor_upload(uint64_t handle, const float* data, uint32_t count);
+AULE_API int32_t aule_tensor_download(uint64_t handle, float* output, uint32_t count);
+AULE_API int32_t aule_tensor_download_u32(uint64_t handle, uint32_t* output, uint32_t count);
+/* lib.zig:626-634 */
+AULE_API uint32_t aule_tensor_size(uint64_t handle);
+/* lib.zig:383-407 */
+AULE_API uint32_t aule_tensor_count(void);
+AULE_API uint32_t aule_tensor_max(void);
+AULE_API void aule_tensor_clear_all(void);
+
+/* lib.zig:496-529  shapes come from the tensors => GQA and Sq != Sk work.
+ * rot_cos/rot_sin must be 0 (RoPE prologue is a SURVEY 8f "next" row): -3.
+ * window_size -1 = full. codes: -1 bad handle, -3 compute error */
+AULE_API int32_t aule_attention_forward_gpu(uint64_t q, uint64_t k, uint64_t v, uint64_t output,
+                                            uint64_t rot_cos, uint64_t rot_sin, int32_t causal,
+                                            int32_t window_size);
+
+/* Out-of-scope product features (SURVEY 2.1 rows 13,14). Exported because
+ * vulkan.py:300-316 sets their prototypes unconditionally; they return -10
+ * ("unsupported") and set the error string.  lib.zig:533-624 */
+AULE_API int32_t aule_attention_forward_paged(uint64_t q, uint64_t k, uint64_t v, uint64_t output,
+                                              uint64_t rot_cos, uint64_t rot_sin, int32_t causal,
+                                              int32_t window_size);
+AULE_API int32_t aule_spatial_sort(uint64_t keys, uint64_t values, uint64_t indices,
+                                   uint32_t sort_dim);
+AULE_API int32_t aule_attention_forward_gravity(uint64_t q, uint64_t k, uint64_t v, uint64_t output,
+                                                uint64_t rot_cos, uint64_t rot_sin, uint64_t indices,
+                                                int32_t causal, uint32_t max_attend,
+                                                int32_t window_size);
+
+/* ------------------------------------------------------------------------ */
+/* Part 2: B200 extension (replaces the slot python/aule/__init__.py:185-207  */
+/* fills with Triton: FlashAttentionTritonFunc, triton_flash.py:386-526)     */
+/* ------------------------------------------------------------------------ */
+
+enum { AULE_DTYPE_F32 = 0, AULE_DTYPE_BF16 = 1, AULE_DTYPE_F16 = 2 };
+
+/* Fused forward on raw device pointers (CUdeviceptr), asynchronous on
+ * `cu_stream` of `device` (no implicit sync).
+ *   q,o: [B,Hq,Sq,D]  k,v: [B,Hkv,Sk,D]  lse_or_0: [B,Hq,Sq] fp32 or 0
+ *   scale <= 0  => 1/sqrt(D)      (triton_flash.py:394-395)
+ *   causal      => key j visible to query i iff j <= i (top-left, :187)
+ *   window      => -1 full; W>0 keeps 0 <= i-j < W (attention_f32.comp:176-178)
+ *   GQA         => kv_head = q_head / (Hq/Hkv)          (triton_flash.py:95-96)
+ * bf16/fp16 with D in {64,128} run the tcgen05/TMA kernel; every other
+ * (dtype, D<=128, D%4==0) runs the fp32-accumulate CUDA-core kernel.
+ * Replaces _flash_attn_fwd_kernel launch, triton_flash.py:448-464. */
+AULE_API int32_t aule_attention_forward_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o,
+                                             uint64_t lse_or_0, uint32_t B, uint32_t Hq, uint32_t Hkv,
+                                             uint32_t Sq, uint32_t Sk, uint32_t D, int32_t dtype,
+                                             float scale, int32_t causal, int32_t window,
+                                             int32_t device, uint64_t cu_stream);
+
+/* Backward on raw device pointers. dq: [B,Hq,Sq,D], dk/dv: [B,Hkv,Sk,D] in
+ * `dtype`; dK/dV are summed over the q-heads of a GQA group on-device
+ * (deterministic, no atomics).  Replaces _compute_delta_kernel +
+ * _flash_attn_bwd_kernel launches, triton_flash.py:495-524. */
+AULE_API int32_t aule_attention_backward_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o,
+                                              uint64_t d_o, uint64_t lse, uint64_t dq, uint64_t dk,
+                                              uint64_t dv, uint32_t B, uint32_t Hq, uint32_t Hkv,
+                                              uint32_t Sq, uint32_t Sk, uint32_t D, int32_t dtype,
+                                              float scale, int32_t causal, int32_t device,
+                                              uint64_t cu_stream);
+
+/* Host-buffer forward for any dtype: stages through device memory with the
+ * H2D copy of batch b+1 / D2H copy of batch b-1 overlapped with the kernel of
+ * batch b (pinned staging, 3 streams).  Synchronous.  lse may be NULL.
+ * This is the call bench.py times for the end-to-end ("e2e") figure. */
+AULE_API int32_t aule_attention_forward_host(const void* q, const void* k, const void* v, void* o,
+                                             float* lse_or_null, uint32_t B, uint32_t Hq,
+                                             uint32_t Hkv, uint32_t Sq, uint32_t Sk, uint32_t D,
+                                             int32_t dtype, float scale, int32_t causal,
+                                             int32_t window, int32_t device);
+
+/* Device bookkeeping. */
+AULE_API int32_t aule_device_count(void);               /* sm_100 devices usable, -1 not init */
+AULE_API int32_t aule_get_sm_count(int32_t device);     /* 148 on B200 */
+AULE_API int32_t aule_synchronize(int32_t device);      /* cuCtxSynchronize on that device */
+/* Launch accounting for tests / bench ("gpu_launches"): number of kernels this
+ * library has launched since init, and the name of the last one. */
+AULE_API uint64_t aule_launch_count(void);
+AULE_API const char* aule_last_kernel(void);
+/* Test hooks. aule_set_kernel_path: 0 = automatic choice, 1 = force the CUDA-core
+ * (fp32-accumulate) kernels for every dtype -- used to cross-check the tensor-core kernel
+ * on the GPU itself.  aule_smoke_multiply: out[i] = 2*in[i] through the whole
+ * module-load / launch / copy path (the tests/test_multiply.zig analogue,
+ * src/compute_pipeline.zig:203-254 + shaders/test.comp). */
+AULE_API int32_t aule_set_kernel_path(int32_t path);
+AULE_API int32_t aule_smoke_multiply(const float* in, float* out, uint32_t n);
+/* Library / ABI version string. */
+AULE_API const char* aule_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AULE_H_ */

@@ -1,0 +1,196 @@
+"""GPU parity for the tcgen05/TMA forward kernel (bf16/fp16, D in {64,128}) and the
+16-bit backward. Expected values: the oracle on the bf16-ROUNDED inputs;
+gate: max|o - o_ref| / max|o_ref| <= 1e-2 (north_star '<=1e-2 rel bf16')."""
+import numpy as np
+import pytest
+
+from conftest import ref_inputs
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def aule():
+    import aule
+    assert aule.get_available_backends() == ["cuda"], aule.get_backend_errors()
+    return aule
+
+
+def _run(aule, q, k, v, causal, dtype, scale=None):
+    import torch
+    from aule import cuda_flash, ffi
+    td = {"bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    tq, tk, tv = (torch.from_numpy(x).cuda().to(td) for x in (q, k, v))
+    out, lse = cuda_flash.forward_with_lse(tq, tk, tv, causal=causal, scale=scale)
+    kern = ffi.load_library().aule_last_kernel().decode()
+    torch.cuda.synchronize()
+    rq, rk, rv = (t.float().cpu().numpy() for t in (tq, tk, tv))          # what the kernel saw
+    return out.float().cpu().numpy(), lse.cpu().numpy(), (rq, rk, rv), kern
+
+
+SHAPES = [
+    # B, Hq, Hkv, Sq, Sk, D, causal
+    (1, 8, 8, 64, 64, 64, True),       # test_triton.py:35-46 shape, fp16/bf16 (:141-152)
+    (1, 8, 8, 64, 64, 128, True),      # test_triton.py:128-139
+    (1, 8, 8, 64, 64, 64, False),
+    (2, 4, 4, 256, 256, 128, True),    # exactly one 256-row work item
+    (1, 2, 2, 128, 128, 64, True),     # second tile entirely out of range
+    (1, 3, 3, 200, 200, 128, True),    # ragged tail inside a tile
+    (2, 8, 2, 384, 384, 128, True),    # GQA 4:1, 1.5 work items
+    (1, 12, 2, 320, 320, 64, True),    # GQA 12/2 (test_triton.py:96-110)
+    (1, 8, 1, 512, 512, 128, True),    # MQA 8/1 (test_triton.py:112-126)
+    (1, 4, 4, 100, 333, 128, False),   # cross attention, ragged Sk (tests/test_cross_attn.py)
+    (1, 2, 2, 700, 700, 64, False),
+    (1, 2, 1, 300, 129, 128, True),    # Sq > Sk causal (columns run out before the diagonal)
+    (1, 2, 2, 1024, 1024, 128, True),  # several KV blocks, lazy-rescale path
+]
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,D,causal", SHAPES)
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_forward_vs_oracle(aule, B, Hq, Hkv, Sq, Sk, D, causal, dtype):
+    q, k, v = ref_inputs(B, Hq, Sq, D, Hkv=Hkv, Sk=Sk)
+    out, lse, (rq, rk, rv), kern = _run(aule, q, k, v, causal, dtype)
+    assert kern == f"aule_fwd_sm100_{dtype}_d{D}", kern
+    exp, exp_lse = orc.attention_ref(rq, rk, rv, causal=causal)
+    assert np.isfinite(out).all()
+    assert orc.rel_err_to_scale(out, exp) <= BF16_TOL, orc.rel_err_to_scale(out, exp)
+    np.testing.assert_allclose(lse, exp_lse, rtol=2e-3, atol=2e-3)
+
+
+def test_large_scores_force_rescale(aule):
+    """Growing row maxima (keys sorted by magnitude) exercise the lazy O-rescale branch."""
+    B, H, S, D = 1, 2, 1024, 128
+    rng = np.random.RandomState(5)
+    q = rng.randn(B, H, S, D).astype(np.float32)
+    k = rng.randn(B, H, S, D).astype(np.float32) * np.linspace(0.2, 6.0, S, dtype=np.float32)[None, None, :, None]
+    v = rng.randn(B, H, S, D).astype(np.float32)
+    out, lse, (rq, rk, rv), kern = _run(aule, q, k, v, False, "bf16")
+    assert "sm100" in kern
+    exp, exp_lse = orc.attention_ref(rq, rk, rv, causal=False)
+    assert orc.rel_err_to_scale(out, exp) <= BF16_TOL
+    np.testing.assert_allclose(lse, exp_lse, rtol=2e-3, atol=2e-2)
+
+
+def test_scale_argument(aule):
+    q, k, v = ref_inputs(1, 2, 300, 128)
+    out, lse, (rq, rk, rv), _ = _run(aule, q, k, v, True, "bf16", scale=0.2)
+    exp, exp_lse = orc.attention_ref(rq, rk, rv, causal=True, scale=0.2)
+    assert orc.rel_err_to_scale(out, exp) <= BF16_TOL
+    np.testing.assert_allclose(lse, exp_lse, rtol=2e-3, atol=2e-3)
+
+
+def test_tensor_core_kernel_agrees_with_cuda_core_kernel(aule):
+    """Same bf16 inputs through both GPU kernels (the CUDA-core one is fp32-exact)."""
+    import torch
+    from aule import cuda_flash, ffi
+    lib = ffi.load_library()
+    torch.manual_seed(42)
+    q = torch.randn(2, 8, 1024, 128, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(2, 2, 1024, 128, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(2, 2, 1024, 128, device="cuda", dtype=torch.bfloat16)
+    o_tc, l_tc = cuda_flash.forward_with_lse(q, k, v, causal=True)
+    assert b"sm100" in lib.aule_last_kernel()
+    lib.aule_set_kernel_path(1)
+    try:
+        o_cc, l_cc = cuda_flash.forward_with_lse(q, k, v, causal=True)
+        assert lib.aule_last_kernel() == b"aule_fwd_simt_bf16"
+    finally:
+        lib.aule_set_kernel_path(0)
+    err = (o_tc.float() - o_cc.float()).abs().max().item() / o_cc.float().abs().max().item()
+    assert err <= BF16_TOL, err
+    assert (l_tc - l_cc).abs().max().item() < 5e-3
+
+
+def test_config_b_sampled_rows(aule):
+    """BASELINE.json configs[1]: bf16 causal MHA [4,32,2048,64]; oracle on sampled (b,h,row-block)."""
+    import torch
+    from aule import cuda_flash
+    torch.manual_seed(42)
+    q, k, v = (torch.randn(4, 32, 2048, 64).to(torch.bfloat16) for _ in range(3))
+    out, lse = cuda_flash.forward_with_lse(q.cuda(), k.cuda(), v.cuda(), causal=True)
+    out, lse = out.float().cpu().numpy(), lse.cpu().numpy()
+    fq, fk, fv = (t.float().numpy() for t in (q, k, v))
+    for (b, h, r0) in ((0, 0, 0), (1, 7, 640), (3, 31, 1920), (2, 16, 1000)):
+        exp, el = orc.attention_rows(fq, fk, fv, b, h, r0, 128, causal=True)
+        assert orc.rel_err_to_scale(out[b, h, r0:r0 + 128], exp) <= BF16_TOL
+        np.testing.assert_allclose(lse[b, h, r0:r0 + 128], el, rtol=2e-3, atol=2e-3)
+
+
+def test_config_c_full_size_properties(aule):
+    """BASELINE.json configs[2] (headline): bf16 GQA 32q/8kv [8,32,4096,128] causal at FULL size.
+    Oracle on sampled row blocks + size-independent properties: batch independence, linearity
+    in V, row 0 == v[0] (top-left causal)."""
+    import torch
+    from aule import cuda_flash
+    g = torch.Generator(device="cuda").manual_seed(42)
+    q = torch.randn(8, 32, 4096, 128, device="cuda", dtype=torch.bfloat16, generator=g)
+    k = torch.randn(8, 8, 4096, 128, device="cuda", dtype=torch.bfloat16, generator=g)
+    v = torch.randn(8, 8, 4096, 128, device="cuda", dtype=torch.bfloat16, generator=g)
+    out, lse = cuda_flash.forward_with_lse(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    # row 0 sees only key 0
+    assert torch.equal(out[:, :, 0, :], v[:, :, 0, :].repeat_interleave(4, dim=1))
+    # sampled oracle checks (GQA: kv head = q head // 4)
+    for (b, h, r0) in ((0, 0, 0), (3, 13, 2048), (7, 31, 3968), (5, 22, 1111)):
+        fq = q[b:b + 1, h:h + 1].float().cpu().numpy()
+        fk = k[b:b + 1, h // 4:h // 4 + 1].float().cpu().numpy()
+        fv = v[b:b + 1, h // 4:h // 4 + 1].float().cpu().numpy()
+        exp, el = orc.attention_rows(fq, fk, fv, 0, 0, r0, 128, causal=True)
+        got = out[b, h, r0:r0 + 128].float().cpu().numpy()
+        assert orc.rel_err_to_scale(got, exp) <= BF16_TOL
+        np.testing.assert_allclose(lse[b, h, r0:r0 + 128].cpu().numpy(), el, rtol=2e-3, atol=2e-3)
+    # batch independence: a single-batch call reproduces that batch bit-for-bit
+    o1, _ = cuda_flash.forward_with_lse(q[2:3], k[2:3], v[2:3], causal=True)
+    assert torch.equal(o1[0], out[2])
+    # linearity in V (bf16 rounding of the sum bounds the error)
+    v2 = torch.randn(1, 8, 4096, 128, device="cuda", dtype=torch.bfloat16, generator=g)
+    oa, _ = cuda_flash.forward_with_lse(q[:1], k[:1], v[:1], causal=True)
+    ob, _ = cuda_flash.forward_with_lse(q[:1], k[:1], v2, causal=True)
+    oc, _ = cuda_flash.forward_with_lse(q[:1], k[:1], (v[:1].float() + v2.float()).to(torch.bfloat16), causal=True)
+    err = (oc.float() - (oa.float() + ob.float())).abs().max().item() / oc.float().abs().max().item()
+    assert err < 3e-2, err
+
+
+def test_config_e_forward_backward_vs_torch_autograd(aule):
+    """BASELINE.json configs[4]: bf16 fwd+bwd [2,16,1024,64] causal; grads vs torch autograd of an
+    fp32 SDPA on the bf16-rounded inputs, tol 1e-2 (python/tests/test_triton.py:66-94)."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(42)
+    q, k, v = (torch.randn(2, 16, 1024, 64, device="cuda").to(torch.bfloat16).requires_grad_() for _ in range(3))
+    out = aule.flash_attention(q, k, v, causal=True)
+    dout = torch.randn_like(out)                                   # test_triton.py:88
+    out.backward(dout)
+    rq, rk, rv = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(rq, rk, rv, is_causal=True)
+    ref.backward(dout.float())
+    assert (out.float() - ref).abs().max().item() / ref.abs().max().item() <= BF16_TOL
+    for g, r in ((q.grad, rq.grad), (k.grad, rk.grad), (v.grad, rv.grad)):
+        err = (g.float() - r).abs().max().item() / r.abs().max().item()
+        assert err <= 1e-2, err
+
+
+def test_sdpa_shim_and_install(aule):
+    """F.scaled_dot_product_attention routed onto the kernel (__init__.py:288-442)."""
+    import torch
+    import torch.nn.functional as F
+    from aule import ffi
+    q = torch.randn(1, 8, 256, 64, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(1, 2, 256, 64, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(1, 2, 256, 64, device="cuda", dtype=torch.bfloat16)
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
+    aule.install()
+    try:
+        n0 = ffi.load_library().aule_launch_count()
+        out = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
+        assert ffi.load_library().aule_launch_count() == n0 + 1
+        masked = F.scaled_dot_product_attention(q, k, v, attn_mask=torch.ones(256, 256, device="cuda", dtype=torch.bool),
+                                                enable_gqa=True)      # falls back to torch
+        assert ffi.load_library().aule_launch_count() == n0 + 1 and masked.shape == q.shape
+    finally:
+        aule.uninstall()
+    assert (out.float() - ref.float()).abs().max().item() <= 2e-2
