@@ -100,6 +100,12 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.fwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem d128)");
     }
+    for (int v = 0; v < 4 && e.empty(); ++v) {
+        e = get(&d.fwd_sm100_var[v], std::string("aule_fwd_sm100_bf16_d128_e") + char('0' + v));
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem variant)");
+    }
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_compute, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
@@ -217,7 +223,12 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         void* params[] = {&tmQ, &tmK, &tmV, &tmO, &p};
         char name[64];
         snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
-        return launch(d, d.fwd_sm100[dtype][d128 ? 1 : 0], name, grid, 1, 1, 512, smem, stream, params);
+        CUfunction fn = d.fwd_sm100[dtype][d128 ? 1 : 0];
+        if (path_ >= kVariantBase && path_ < kVariantBase + 4 && dtype == kBF16 && d128) {
+            fn = d.fwd_sm100_var[path_ - kVariantBase];
+            snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d128_e%d", path_ - kVariantBase);
+        }
+        return launch(d, fn, name, grid, 1, 1, 512, smem, stream, params);
     }
     SimtParams p;
     memset(&p, 0, sizeof(p));

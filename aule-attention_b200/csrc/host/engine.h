@@ -29,7 +29,7 @@ struct AttnShape {
     uint32_t B, Hq, Hkv, Sq, Sk, D;
 };
 
-enum KernelPath : int32_t { kAuto = 0, kForceCudaCore = 1 };
+enum KernelPath : int32_t { kAuto = 0, kForceCudaCore = 1, kVariantBase = 16 /* 16+v: bf16 d128 tuning variant v */ };
 
 struct Device {
     int ordinal = -1;
@@ -43,6 +43,7 @@ struct Device {
     CUfunction bwd_dq_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dkv_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
+    CUfunction fwd_sm100_var[4] = {nullptr, nullptr, nullptr, nullptr};   // bf16 d128 tuning variants (_e0.._e3)
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;

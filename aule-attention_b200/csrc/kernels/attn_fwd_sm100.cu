@@ -40,8 +40,9 @@ using aule_kp::FwdParams;
 template <int D> using Cfg = aule_kp::FwdCfg<D>;
 
 // barrier indices
-enum : int { B_QFULL = 0, B_QEMPTY = 2, B_SFULL = 4, B_PFULL = 6, B_OFULL = 8, B_OEMPTY = 10,
-             B_STFULL = 12, B_STEMPTY = 14, B_KVFULL = 16 /* + NS: kv_empty */ };
+enum : int { B_QFULL = 0, B_QEMPTY = 2, B_SFULL = 4, B_PFULL = 6 /* P columns [0,48): keys 0..95 */, B_OFULL = 8,
+             B_OEMPTY = 10, B_STFULL = 12, B_STEMPTY = 14, B_PFULLB = 16 /* P columns [48,64): keys 96..127 */,
+             B_KVFULL = 18 /* + NS: kv_empty */ };
 
 struct Work {
     uint32_t bh, bkv, row0, n0, n1;
@@ -69,7 +70,7 @@ struct Ring {
     }
 };
 
-template <int D, bool BF16>
+template <int D, bool BF16, int EMU4>
 __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
                                          const CUtensorMap* tmO, const FwdParams& p) {
     using C = Cfg<D>;
@@ -89,6 +90,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             mbar_init(bar(B_QEMPTY + t), 1);    // tcgen05.commit
             mbar_init(bar(B_SFULL + t), 1);     // tcgen05.commit
             mbar_init(bar(B_PFULL + t), 128);   // softmax threads
+            mbar_init(bar(B_PFULLB + t), 128);  // softmax threads
             mbar_init(bar(B_OFULL + t), 1);     // tcgen05.commit
             mbar_init(bar(B_OEMPTY + t), 128);  // epilogue threads
             mbar_init(bar(B_STFULL + t), 128);  // softmax threads
@@ -174,26 +176,39 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     }
                 }
                 const float neg_ms = (m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2;
-                float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+                // P = exp2(s*scale_log2 - m*scale_log2), two values per instruction (f32x2). EMU4 of every 4
+                // pairs take the polynomial path (FMA/ALU pipes) instead of MUFU.EX2, which is the pipe that
+                // otherwise paces this kernel (16 ex2/clk/SM against 8192 MMA flop/clk/SM).
+                const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float p0 = ex2(fmaf(__uint_as_float(s[c][2 * i]), p.scale_log2, neg_ms));
-                        const float p1 = ex2(fmaf(__uint_as_float(s[c][2 * i + 1]), p.scale_log2, neg_ms));
-                        const float p2 = ex2(fmaf(__uint_as_float(s[c][2 * i + 2]), p.scale_log2, neg_ms));
-                        const float p3 = ex2(fmaf(__uint_as_float(s[c][2 * i + 3]), p.scale_log2, neg_ms));
-                        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
-                        pk[i] = pack2<BF16>(p0, p1);
-                        pk[i + 1] = pack2<BF16>(p2, p3);
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+                        float2 e;
+                        if ((i & 3) < EMU4) {
+                            e = ex2_emu2(x);
+                        } else {
+                            e.x = ex2(x.x);
+                            e.y = ex2(x.y);
+                        }
+                        if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
+                        pk[i] = pack2<BF16>(e.x, e.y);
                     }
                     tmem_st16(tS + c * 16, pk);                     // P_t: 32 values -> 16 columns
+                    if (c == 2) {                                   // keys 0..95 ready: PV k-steps 0..5 may start
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(bar(B_PFULL + t));
+                    }
                 }
-                l += (sum0 + sum1) + (sum2 + sum3);
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(bar(B_PFULL + t));
+                mbar_arrive(bar(B_PFULLB + t));
+                const float2 acc = __fadd2_rn(acc0, acc1);
+                l += acc.x + acc.y;
             }
             // hand the row statistics to the epilogue warps
             mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
@@ -280,13 +295,14 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         mma_ss(d, mk(HI_K_HI, a_lo + off), mk(HI_K_HI, b_lo + off), IDESC_QK, kk > 0);
                     }
                 };
-                auto issue_pv = [&](uint32_t t, uint32_t vstage, bool acc) {
+                auto issue_pv = [&](uint32_t t, uint32_t vstage, bool acc, int k0, int k1) {
                     const uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
                     const uint32_t a = tmem + (t ? C::COL_S1 : C::COL_S0);
                     const uint32_t d = tmem + (t ? C::COL_O1 : C::COL_O0);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (acc || kk > 0) ? 1u : 0u);
+                        if (kk >= k0 && kk < k1)
+                            mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (acc || kk > 0) ? 1u : 0u);
                 };
                 for (uint32_t w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
                     const Work wk = decode(p, w);
@@ -316,10 +332,13 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             const uint32_t nt = t ? wk.n1 : wk.n0;
                             if (j >= nt) continue;
                             uint32_t& cp = t ? cp1 : cp0;
-                            mbar_wait(bar(B_PFULL + t), cp & 1); ++cp;
+                            mbar_wait(bar(B_PFULL + t), cp & 1);
                             if (j == 0) mbar_wait(bar(B_OEMPTY + t), (it & 1) ^ 1);
                             tc_fence_after();
-                            issue_pv(t, vstage, j > 0);
+                            issue_pv(t, vstage, j > 0, 0, 6);
+                            mbar_wait(bar(B_PFULLB + t), cp & 1); ++cp;
+                            tc_fence_after();
+                            issue_pv(t, vstage, j > 0, 6, 8);
                             if (j == nt - 1) mma_commit(bar(B_OFULL + t));
                             if (t == 1) mma_commit(bar(B_KVFULL + NS + vstage));     // V_j: tile 1 is the last user
                             if (j + 1 < nt) {
@@ -375,16 +394,24 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 
 }  // namespace fwd100
 
-#define AULE_FWD100(NAME, DD, BF)                                                                       \
+#define AULE_FWD100(NAME, DD, BF, EMU)                                                                  \
     extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
                                                               const __grid_constant__ CUtensorMap tmO,   \
-                                                              const fwd100::FwdParams p) {               \
-        fwd100::fwd_body<DD, BF>(&tmQ, &tmK, &tmV, &tmO, p);                                             \
+                                                              const aule_kp::FwdParams p) {              \
+        fwd100::fwd_body<DD, BF, EMU>(&tmQ, &tmK, &tmV, &tmO, p);                                        \
     }
 
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false)
+#ifndef AULE_FWD_EMU4
+#define AULE_FWD_EMU4 1          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
+#endif
+AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4)
+AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4)
+AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4)
+AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4)
+// tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + EMU4))
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0)
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1)
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 2)
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e3, 128, true, 3)

@@ -40,7 +40,7 @@ struct FwdCfg {
     static constexpr uint32_t OFF_O = OFF_KV + NS * TILE_BYTES;
     static constexpr uint32_t OFF_STAT = OFF_O + 2 * TILE_BYTES;   // float l[2][128], m[2][128]
     static constexpr uint32_t OFF_BAR = OFF_STAT + 4 * 128 * 4;
-    static constexpr int NBAR = 16 + 2 * NS;
+    static constexpr int NBAR = 18 + 2 * NS;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
     // TMEM columns

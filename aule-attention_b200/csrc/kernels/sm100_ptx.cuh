@@ -44,10 +44,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000000u)     // suspend-time hint (ns): idle roles sleep instead of spinning
         : "memory");
     return ok != 0;
 }
@@ -217,6 +217,32 @@ __device__ __forceinline__ float lg2(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// exp2 for a pair on the FMA/ALU pipes (no MUFU): Cody-Waite split x = floor(x) + f, degree-3
+// polynomial for 2^f on [0,1) (max rel. error ~1e-4, far below the bf16 rounding of P), exponent
+// patched in with an integer add.  Valid for x <= 127; x < -127 is clamped (result ~1e-38 ~ 0).
+__device__ __forceinline__ float2 ex2_emu2(float2 x) {
+    const float magic = 12582912.f;                       // 2^23 + 2^22
+    x.x = fmaxf(x.x, -127.f);
+    x.y = fmaxf(x.y, -127.f);
+    float2 xr;                                            // x + magic, rounded DOWN: floor(x) in the low mantissa bits
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 b, {%4, %4};\n\t"
+        "add.rm.ftz.f32x2 d, a, b;\n\t"
+        "mov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(xr.x), "=f"(xr.y)
+        : "f"(x.x), "f"(x.y), "f"(magic));
+    const float2 fl = __fadd2_rn(xr, make_float2(-magic, -magic));            // floor(x) as float
+    const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);               // fractional part in [0,1)
+    float2 p = __ffma2_rn(f, make_float2(0.077119089663028717041015625f, 0.077119089663028717041015625f),
+                          make_float2(0.227564394474029541015625f, 0.227564394474029541015625f));
+    p = __ffma2_rn(p, f, make_float2(0.695146143436431884765625f, 0.695146143436431884765625f));
+    p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xr.x) << 23));
+    r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23));
+    return r;
 }
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
