@@ -63,6 +63,16 @@ __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     return t;
 }
 
+// Static persistent schedule: work items are sorted heaviest-first (decode) and dealt to the CTAs in
+// boustrophedon ("snake") order, round r going left-to-right when even and right-to-left when odd, which
+// balances the monotonically decreasing causal weights to ~0.3% (plain round-robin: 3.4% on config C).
+__device__ __forceinline__ bool next_work(const FwdParams& p, uint32_t it, uint32_t& w) {
+    const uint32_t base = it * gridDim.x;
+    if (base >= p.num_tiles) return false;
+    w = base + ((it & 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x);
+    return w < p.num_tiles;          // only the last round can be partial
+}
+
 struct Ring {
     uint32_t stage = 0, phase = 0;
     template <int NS> __device__ __forceinline__ void advance() {
@@ -123,7 +133,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         const uint32_t tS = tmem + lane_addr + (t ? C::COL_S1 : C::COL_S0);
         const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
         uint32_t cs = 0, it = 0;
-        for (uint32_t w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
+        for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             const uint32_t n = t ? wk.n1 : wk.n0;
             const uint32_t trow0 = wk.row0 + t * 128;
@@ -223,7 +233,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
         const bool issuer = (warp == 8 && lane == 0);
         uint32_t it = 0;
-        for (uint32_t w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
+        for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
@@ -304,7 +314,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         if (kk >= k0 && kk < k1)
                             mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (acc || kk > 0) ? 1u : 0u);
                 };
-                for (uint32_t w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
+                for (uint32_t w; next_work(p, it, w); ++it) {
                     const Work wk = decode(p, w);
                     const uint32_t nmax = wk.n1;                    // n0 <= n1
                     // ---- prologue: S_t(0) = Q_t K_0^T
@@ -367,7 +377,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         tma_load_3d(dst + c * C::CHUNK_BYTES, map, full, c * 64, (int32_t)(j * 128), (int32_t)bkv);
                     ring.advance<NS>();
                 };
-                for (uint32_t w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
+                for (uint32_t w; next_work(p, it, w); ++it) {
                     const Work wk = decode(p, w);
                     load_kv(tmK, 0, wk.bkv);
                     for (uint32_t t = 0; t < 2; ++t) {
@@ -404,7 +414,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     }
 
 #ifndef AULE_FWD_EMU4
-#define AULE_FWD_EMU4 1          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
+#define AULE_FWD_EMU4 0          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
 #endif
 AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4)
 AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4)
