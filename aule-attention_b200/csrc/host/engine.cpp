@@ -100,11 +100,15 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.fwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem d128)");
     }
+    static const char* kVariants[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
+                                       "aule_fwd_sm100_bf16_d128_v3", nullptr};
     for (int v = 0; v < 4 && e.empty(); ++v) {
-        e = get(&d.fwd_sm100_var[v], std::string("aule_fwd_sm100_bf16_d128_e") + char('0' + v));
+        if (!kVariants[v]) continue;
+        e = get(&d.fwd_sm100_var[v], kVariants[v]);
+        const int smem = (v == 2) ? (int)aule_kp::FwdCfgV3<128>::SMEM_BYTES : (int)FwdCfg<128>::SMEM_BYTES;
         if (e.empty())
-            e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                              (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem variant)");
+            e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem),
+                      "cuFuncSetAttribute(smem variant)");
     }
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
@@ -224,11 +228,15 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         char name[64];
         snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
         CUfunction fn = d.fwd_sm100[dtype][d128 ? 1 : 0];
-        if (path_ >= kVariantBase && path_ < kVariantBase + 4 && dtype == kBF16 && d128) {
+        unsigned smem_use = smem;
+        if (path_ >= kVariantBase && path_ < kVariantBase + 4 && dtype == kBF16 && d128 && d.fwd_sm100_var[path_ - kVariantBase]) {
+            static const char* kNames[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
+                                            "aule_fwd_sm100_bf16_d128_v3", ""};
             fn = d.fwd_sm100_var[path_ - kVariantBase];
-            snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d128_e%d", path_ - kVariantBase);
+            snprintf(name, sizeof(name), "%s", kNames[path_ - kVariantBase]);
+            if (path_ - kVariantBase == 2) smem_use = aule_kp::FwdCfgV3<128>::SMEM_BYTES;
         }
-        return launch(d, fn, name, grid, 1, 1, 512, smem, stream, params);
+        return launch(d, fn, name, grid, 1, 1, 512, smem_use, stream, params);
     }
     SimtParams p;
     memset(&p, 0, sizeof(p));

@@ -1,4 +1,4 @@
-// Fused FlashAttention-2 forward for sm_100a (B200): TMA -> SMEM -> tcgen05.mma -> TMEM.   (kernel v4)
+// Fused FlashAttention-2 forward for sm_100a (B200): TMA -> SMEM -> tcgen05.mma -> TMEM.
 //
 // Replaces (behaviour, not code) the reference's forward kernels:
 //   python/aule/triton_flash.py:62-235 (_flash_attn_fwd_kernel),
@@ -6,58 +6,43 @@
 // Semantics kept: O = softmax(scale*QK^T + mask) V; top-left causal mask (j <= i,
 // triton_flash.py:187); GQA kv_head = q_head / (Hq/Hkv) (:95-96); LSE = m + ln(l) (:232).
 //
-// One persistent CTA per SM (512 threads) looping over work items (256 query rows = two
-// 128-row tiles of one (batch, q-head)), heaviest first, dealt in snake order:
+// One persistent CTA per SM (512 threads), each looping over work items
+// (256 query rows = two 128-row tiles of one (batch, q-head)), heaviest first:
 //
-//   warps 0-3   softmax, tile 0   (thread == query row: S TMEM -> registers, exp2, P -> TMEM)
-//   warps 4-7   softmax, tile 1
-//   warps 8-11  epilogue          (O: TMEM -> regs -> 1/l -> SMEM -> TMA store; LSE)
-//   warp  12    MMA issuer        (one elected thread issues every tcgen05.mma)
-//   warp  13    TMA producer      (one elected thread issues every bulk tensor load)
+//   warps 0-3   softmax for tile 0   (thread == query row; S read from TMEM, P written
+//   warps 4-7   softmax for tile 1    back to TMEM as bf16/fp16; lazy O rescale in place)
+//   warps 8-11  epilogue              (O: TMEM -> regs -> 1/l -> SMEM -> TMA store; LSE)
+//   warp  12    MMA issuer            (one elected thread issues every tcgen05.mma)
+//   warp  13    TMA producer          (one elected thread issues every bulk tensor load)
 //   warp  14    TMEM allocator
 //
-// TMEM (512 columns): S [0,128) shared by both tiles | P0 [128,192) | P1 [192,256) |
-//                     O0 [256,256+D) | O1 [256+D,256+2D).
-// S only lives from the end of Q K^T until the softmax warps have copied it to registers
-// (~150 cycles), so ONE S buffer serves both tiles and P gets columns of its own.  That removes the
-// S/P aliasing of v3 and with it the serial chain  softmax(j) -> P V -> Q K^T(j+1) -> softmax(j+1):
-// the next Q K^T of a tile is issued as soon as the OTHER tile's softmax has drained S, and runs
-// under this tile's exp phase, so the softmax warps (the MUFU-bound stage) never wait for it.
-// Steady-state issue order of the MMA thread (all waits blocking, order == readiness order):
-//     PV_0(j)  QK_1(j+1)  PV_1(j)  QK_0(j+2)  PV_0(j+1)  QK_1(j+2)  ...
-// Hazards: P_t is rewritten for block j+1 only after pv_done[t] (commit after PV_t(j)); the rare
-// in-place O_t rescale waits for the same barrier; S is handed over through s_free (128 arrivals
-// after the tcgen05.ld of S completes).
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D).
+// P_t aliases the first 64 columns of S_t (two 16-bit values per 32-bit column).
+// The two tiles ping-pong: while the softmax warps of one tile run exp2 on S_t(j), the
+// tensor core runs P V and the next Q K^T of the other tile
+//   (issue order: QK0(0) QK1(0) | PV0(0) QK0(1) | PV1(0) QK1(1) | PV0(1) QK0(2) | ...).
+// tcgen05.mma's issued by one thread execute in order, which is what protects the
+// S_t/P_t aliasing (PV_t(j) is always issued before QK_t(j+1)).
 //
-// SMEM (D=128): Q 2x32 KB | K/V ring 4x32 KB (load order K0 K1 V0 K2 V1 K3 ...) | O staging 32 KB |
-// row statistics 2 KB | mbarriers.  All operand tiles are [128 rows][64 elements] 128B-swizzled
-// sub-tiles (TMA box 64x128): the K-major canonical UMMA layout for Q/K and the MN-major one for V.
+// SMEM (D=128): Q 2x32 KB, K/V ring 3x32 KB (K and V tiles share the ring, load order
+// K0 V0 K1 V1 ...), O staging 2x32 KB, row statistics 2 KB, mbarriers.  All operand tiles are
+// [128 rows][64 elements] 128B-swizzled sub-tiles (TMA box 64x128), which is at once the
+// K-major canonical layout for Q/K and the MN-major canonical layout for V.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "sm100_ptx.cuh"
 #include "kernel_params.h"
 
-namespace fwd100 {
+namespace fwd100v3 {
 using namespace sm100;
 using aule_kp::FwdParams;
-template <int D> using Cfg = aule_kp::FwdCfg<D>;
+template <int D> using Cfg = aule_kp::FwdCfgV3<D>;
 
-// barrier indices (pairs are indexed by tile)
-enum : int {
-    B_QFULL = 0,     // TMA -> MMA: Q_t landed
-    B_QEMPTY = 2,    // MMA -> TMA: last QK_t of the work item done (commit)
-    B_SFULL = 4,     // MMA -> softmax t: S holds Q_t K^T (commit)
-    B_PFULL = 6,     // softmax t -> MMA: P_t columns [0,48) written (keys 0..95)
-    B_PFULLB = 8,    // softmax t -> MMA: P_t columns [48,64) written (keys 96..127)
-    B_PVDONE = 10,   // MMA -> softmax t: PV_t(j) complete (commit): P_t / O_t may be touched
-    B_OFULL = 12,    // MMA -> epilogue: last PV_t of the work item done (commit)
-    B_OEMPTY = 14,   // epilogue -> MMA: O_t drained from TMEM
-    B_STFULL = 16,   // softmax t -> epilogue: row statistics written
-    B_STEMPTY = 18,  // epilogue -> softmax t: row statistics consumed
-    B_SFREE = 20,    // softmax (either tile) -> MMA: S copied to registers
-    B_KVFULL = 21    // + NS: kv_empty
-};
+// barrier indices
+enum : int { B_QFULL = 0, B_QEMPTY = 2, B_SFULL = 4, B_PFULL = 6 /* P columns [0,48): keys 0..95 */, B_OFULL = 8,
+             B_OEMPTY = 10, B_STFULL = 12, B_STEMPTY = 14, B_PFULLB = 16 /* P columns [48,64): keys 96..127 */,
+             B_KVFULL = 18 /* + NS: kv_empty */ };
 
 struct Work {
     uint32_t bh, bkv, row0, n0, n1;
@@ -116,13 +101,11 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             mbar_init(bar(B_SFULL + t), 1);     // tcgen05.commit
             mbar_init(bar(B_PFULL + t), 128);   // softmax threads
             mbar_init(bar(B_PFULLB + t), 128);  // softmax threads
-            mbar_init(bar(B_PVDONE + t), 1);    // tcgen05.commit
             mbar_init(bar(B_OFULL + t), 1);     // tcgen05.commit
             mbar_init(bar(B_OEMPTY + t), 128);  // epilogue threads
             mbar_init(bar(B_STFULL + t), 128);  // softmax threads
             mbar_init(bar(B_STEMPTY + t), 128); // epilogue threads
         }
-        mbar_init(bar(B_SFREE), 128);           // softmax threads of whichever tile owns S
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_KVFULL + s), 1);
             mbar_init(bar(B_KVFULL + NS + s), 1);
@@ -147,25 +130,22 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         const uint32_t t = warp >> 2;                               // tile 0 / 1
         const uint32_t r = (warp & 3) * 32 + lane;                  // row within the tile == TMEM lane
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem + lane_addr + C::COL_S;
-        const uint32_t tP = tmem + lane_addr + (t ? C::COL_P1 : C::COL_P0);
+        const uint32_t tS = tmem + lane_addr + (t ? C::COL_S1 : C::COL_S0);
         const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
-        uint32_t g = 0, it = 0;                                     // g: blocks processed so far by this tile
+        uint32_t cs = 0, it = 0;
         for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             const uint32_t n = t ? wk.n1 : wk.n0;
             const uint32_t trow0 = wk.row0 + t * 128;
             const uint32_t grow = trow0 + r;                        // global query row
             float m_used = -INFINITY, l = 0.f;
-            for (uint32_t j = 0; j < n; ++j, ++g) {
-                mbar_wait(bar(B_SFULL + t), g & 1);
+            for (uint32_t j = 0; j < n; ++j) {
+                mbar_wait(bar(B_SFULL + t), cs & 1); ++cs;
                 tc_fence_after();
                 uint32_t s[4][32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
                 tmem_wait_ld();
-                tc_fence_before();
-                mbar_arrive(bar(B_SFREE));                          // S may be overwritten by the next Q K^T
                 const bool need_mask = (p.causal && j * 128 + 127 > trow0) || ((j + 1) * 128 > p.Sk);
                 if (need_mask) {
                     const uint32_t lim = p.causal ? min(grow, p.Sk - 1) : p.Sk - 1;   // last visible key
@@ -189,15 +169,11 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 // Lazy rescale: adopt the new maximum only when it grew by more than 2^8 in the
                 // exp2 domain; otherwise P stays <= 256, harmless in bf16/fp16 and fp32 sums.
                 const bool grow_max = (m_new - m_used) * p.scale_log2 > 8.f;   // m_used = -inf -> true
-                bool pv_waited = false;
                 if (__any_sync(0xffffffffu, grow_max)) {
                     const float alpha = grow_max ? ex2((m_used - m_new) * p.scale_log2) : 1.f;
                     l *= alpha;
                     if (grow_max) m_used = m_new;
-                    if (j > 0) {
-                        mbar_wait(bar(B_PVDONE + t), (g - 1) & 1);   // PV_t(j-1) complete: O_t is stable
-                        pv_waited = true;
-                        tc_fence_after();
+                    if (j > 0) {                                    // O_t(j-1) is complete (s_full tracks all prior MMAs)
 #pragma unroll 1
                         for (int c = 0; c < D / 32; ++c) {
                             uint32_t o[32];
@@ -211,12 +187,13 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 }
                 const float neg_ms = (m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2;
                 // P = exp2(s*scale_log2 - m*scale_log2), two values per instruction (f32x2). EMU4 of every 4
-                // pairs may take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
+                // pairs take the polynomial path (FMA/ALU pipes) instead of MUFU.EX2, which is the pipe that
+                // otherwise paces this kernel (16 ex2/clk/SM against 8192 MMA flop/clk/SM).
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-                uint32_t pk[2][16];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
@@ -228,27 +205,18 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             e.y = ex2(x.y);
                         }
                         if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
-                        pk[c & 1][i] = pack2<BF16>(e.x, e.y);
+                        pk[i] = pack2<BF16>(e.x, e.y);
                     }
-                    if (c == 1) {
-                        // P_t is still being read by PV_t of the previous block until pv_done: the first
-                        // two chunks are computed under that MMA and stored once it has finished.
-                        if (g > 0 && !pv_waited) mbar_wait(bar(B_PVDONE + t), (g - 1) & 1);
-                        tc_fence_after();
-                        tmem_st16(tP, pk[0]);
-                        tmem_st16(tP + 16, pk[1]);
-                    } else if (c == 2) {
-                        tmem_st16(tP + 32, pk[0]);                   // keys 0..95 ready: PV k-steps 0..5 may start
+                    tmem_st16(tS + c * 16, pk);                     // P_t: 32 values -> 16 columns
+                    if (c == 2) {                                   // keys 0..95 ready: PV k-steps 0..5 may start
                         tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(bar(B_PFULL + t));
-                    } else if (c == 3) {
-                        tmem_st16(tP + 48, pk[1]);
-                        tmem_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(bar(B_PFULLB + t));
                     }
                 }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar(B_PFULLB + t));
                 const float2 acc = __fadd2_rn(acc0, acc1);
                 l += acc.x + acc.y;
             }
@@ -264,19 +232,19 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         const uint32_t r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
         const bool issuer = (warp == 8 && lane == 0);
-        const uint32_t sO = sb + C::OFF_O;
         uint32_t it = 0;
         for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
+                const uint32_t sO = sb + C::OFF_O + t * C::TILE_BYTES;
                 mbar_wait(bar(B_STFULL + t), it & 1);
                 const float l = sStat[t * 128 + r];
                 const float m = sStat[256 + t * 128 + r];
                 mbar_arrive(bar(B_STEMPTY + t));
                 mbar_wait(bar(B_OFULL + t), it & 1);
                 tc_fence_after();
-                if (issuer) tma_store_wait_read<0>();               // the previous store has finished reading sO
+                if (issuer) tma_store_wait_read<1>();               // the store that last read sO[t] is done
                 named_bar_sync(1, 128);
                 const float inv = 1.f / l;
 #pragma unroll
@@ -320,94 +288,77 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         if (warp == 12) {
             // ================================================= MMA issuer
             if (elect_one()) {
-                Ring ring;                                          // next K/V ring slot to acquire
-                uint32_t gpv0 = 0, gpv1 = 0;                        // PV_t issued so far (parity of p_full / p_fullb)
-                uint32_t nqk = 0;                                   // Q K^T issued so far (parity of s_free)
-                uint32_t it = 0;
+                Ring ring;
+                uint32_t cp0 = 0, cp1 = 0, it = 0;
                 // Descriptors are (constant high word, low word = const | addr>>4); stepping along K
                 // is an immediate add on the low word (the 14-bit address field never carries).
                 constexpr uint32_t HI_K_HI = uint32_t(HI_K >> 32), HI_K_LO = uint32_t(HI_K);
                 constexpr uint32_t HI_V_HI = uint32_t(HI_V >> 32), HI_V_LO = uint32_t(HI_V);
                 auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
-                auto acquire = [&]() -> uint32_t {                  // wait for the next tile of the load order
-                    const uint32_t st = ring.stage;
-                    mbar_wait(bar(B_KVFULL + st), ring.phase);
-                    ring.advance<NS>();
-                    return st;
-                };
-                auto issue_qk = [&](uint32_t t, uint32_t kstage) {  // S = Q_t K^T (waits until S has been drained)
-                    if (nqk > 0) mbar_wait(bar(B_SFREE), (nqk - 1) & 1);
-                    ++nqk;
-                    tc_fence_after();
+                auto issue_qk = [&](uint32_t t, uint32_t kstage) {
                     const uint32_t a_lo = HI_K_LO | ((sb + C::OFF_Q + t * C::TILE_BYTES) >> 4);
                     const uint32_t b_lo = HI_K_LO | ((sb + C::OFF_KV + kstage * C::TILE_BYTES) >> 4);
-                    const uint32_t d = tmem + C::COL_S;
+                    const uint32_t d = tmem + (t ? C::COL_S1 : C::COL_S0);
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk) {
                         const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
                         mma_ss(d, mk(HI_K_HI, a_lo + off), mk(HI_K_HI, b_lo + off), IDESC_QK, kk > 0);
                     }
-                    mma_commit(bar(B_SFULL + t));
                 };
-                auto issue_pv = [&](uint32_t t, uint32_t vstage, bool first, bool last) {   // O_t (+)= P_t V
-                    uint32_t& gpv = t ? gpv1 : gpv0;
+                auto issue_pv = [&](uint32_t t, uint32_t vstage, bool acc, int k0, int k1) {
                     const uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
-                    const uint32_t a = tmem + (t ? C::COL_P1 : C::COL_P0);
+                    const uint32_t a = tmem + (t ? C::COL_S1 : C::COL_S0);
                     const uint32_t d = tmem + (t ? C::COL_O1 : C::COL_O0);
-                    mbar_wait(bar(B_PFULL + t), gpv & 1);
-                    if (first) mbar_wait(bar(B_OEMPTY + t), (it & 1) ^ 1);   // epilogue drained the previous O_t
-                    tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 6; ++kk)
-                        mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (!first || kk > 0) ? 1u : 0u);
-                    mbar_wait(bar(B_PFULLB + t), gpv & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int kk = 6; kk < 8; ++kk)
-                        mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, 1u);
-                    ++gpv;
-                    mma_commit(bar(B_PVDONE + t));
-                    if (last) mma_commit(bar(B_OFULL + t));
+                    for (int kk = 0; kk < 8; ++kk)
+                        if (kk >= k0 && kk < k1)
+                            mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (acc || kk > 0) ? 1u : 0u);
                 };
                 for (uint32_t w; next_work(p, it, w); ++it) {
                     const Work wk = decode(p, w);
-                    const uint32_t n0 = wk.n0, n1 = wk.n1;          // n0 <= n1, n1 >= 1
-                    // ---- prologue: QK_0(0) QK_1(0) QK_0(1)
-                    uint32_t k_cur = acquire();                     // K_0
-                    mbar_wait(bar(B_QFULL + 0), it & 1);
-                    issue_qk(0, k_cur);
-                    if (n0 == 1) mma_commit(bar(B_QEMPTY + 0));
-                    mbar_wait(bar(B_QFULL + 1), it & 1);
-                    issue_qk(1, k_cur);
-                    if (n1 == 1) mma_commit(bar(B_QEMPTY + 1));
-                    mma_commit(bar(B_KVFULL + NS + k_cur));         // K_0 released
-                    uint32_t k_next = 0, k_next2 = 0;               // stages of K_{j+1}, K_{j+2}
-                    if (n1 > 1) {
-                        k_next = acquire();                         // K_1
-                        if (1 < n0) {
-                            issue_qk(0, k_next);
-                            if (n0 == 2) mma_commit(bar(B_QEMPTY + 0));
-                        }
+                    const uint32_t nmax = wk.n1;                    // n0 <= n1
+                    // ---- prologue: S_t(0) = Q_t K_0^T
+                    uint32_t kstage = ring.stage;
+                    mbar_wait(bar(B_KVFULL + kstage), ring.phase);
+                    ring.advance<NS>();
+                    for (uint32_t t = 0; t < 2; ++t) {
+                        mbar_wait(bar(B_QFULL + t), it & 1);
+                        tc_fence_after();
+                        issue_qk(t, kstage);
+                        mma_commit(bar(B_SFULL + t));
+                        if ((t ? wk.n1 : wk.n0) == 1) mma_commit(bar(B_QEMPTY + t));
                     }
+                    mma_commit(bar(B_KVFULL + NS + kstage));
                     // ---- main loop
-                    for (uint32_t j = 0; j < n1; ++j) {
-                        const uint32_t v = acquire();               // V_j
-                        if (j < n0) issue_pv(0, v, j == 0, j == n0 - 1);
-                        if (j + 1 < n1) {
-                            issue_qk(1, k_next);                    // QK_1(j+1): last user of K_{j+1}
-                            if (j + 1 == n1 - 1) mma_commit(bar(B_QEMPTY + 1));
-                            mma_commit(bar(B_KVFULL + NS + k_next));
-                        }
-                        issue_pv(1, v, j == 0, j == n1 - 1);
-                        mma_commit(bar(B_KVFULL + NS + v));         // V_j released
-                        if (j + 2 < n1) {
-                            k_next2 = acquire();                    // K_{j+2}
-                            if (j + 2 < n0) {
-                                issue_qk(0, k_next2);
-                                if (j + 2 == n0 - 1) mma_commit(bar(B_QEMPTY + 0));
+                    for (uint32_t j = 0; j < nmax; ++j) {
+                        const uint32_t vstage = ring.stage;
+                        mbar_wait(bar(B_KVFULL + vstage), ring.phase);
+                        ring.advance<NS>();
+                        const bool has_k = (j + 1 < nmax);
+                        const uint32_t kst = ring.stage, kph = ring.phase;
+                        bool k_ready = false;
+                        if (has_k) ring.advance<NS>();
+                        for (uint32_t t = 0; t < 2; ++t) {
+                            const uint32_t nt = t ? wk.n1 : wk.n0;
+                            if (j >= nt) continue;
+                            uint32_t& cp = t ? cp1 : cp0;
+                            mbar_wait(bar(B_PFULL + t), cp & 1);
+                            if (j == 0) mbar_wait(bar(B_OEMPTY + t), (it & 1) ^ 1);
+                            tc_fence_after();
+                            issue_pv(t, vstage, j > 0, 0, 6);
+                            mbar_wait(bar(B_PFULLB + t), cp & 1); ++cp;
+                            tc_fence_after();
+                            issue_pv(t, vstage, j > 0, 6, 8);
+                            if (j == nt - 1) mma_commit(bar(B_OFULL + t));
+                            if (t == 1) mma_commit(bar(B_KVFULL + NS + vstage));     // V_j: tile 1 is the last user
+                            if (j + 1 < nt) {
+                                if (!k_ready) { mbar_wait(bar(B_KVFULL + kst), kph); tc_fence_after(); k_ready = true; }
+                                issue_qk(t, kst);
+                                mma_commit(bar(B_SFULL + t));
+                                if (j + 1 == nt - 1) mma_commit(bar(B_QEMPTY + t));
+                                if (t == 1) mma_commit(bar(B_KVFULL + NS + kst));    // K_{j+1}: same
                             }
                         }
-                        k_next = k_next2;
                     }
                 }
             }
@@ -438,10 +389,9 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             tma_load_3d(sb + C::OFF_Q + t * C::TILE_BYTES + c * C::CHUNK_BYTES, tmQ, full, c * 64,
                                         (int32_t)(wk.row0 + t * 128), (int32_t)wk.bh);
                     }
-                    if (wk.n1 > 1) load_kv(tmK, 1, wk.bkv);         // same order as the MMA thread acquires
                     for (uint32_t j = 0; j < wk.n1; ++j) {
                         load_kv(tmV, j, wk.bkv);
-                        if (j + 2 < wk.n1) load_kv(tmK, j + 2, wk.bkv);
+                        if (j + 1 < wk.n1) load_kv(tmK, j + 1, wk.bkv);
                     }
                 }
             }
@@ -452,24 +402,17 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     if (warp == 14) tmem_dealloc<512>(tmem);
 }
 
-}  // namespace fwd100
+}  // namespace fwd100v3
 
+#undef AULE_FWD100
 #define AULE_FWD100(NAME, DD, BF, EMU)                                                                  \
     extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
                                                               const __grid_constant__ CUtensorMap tmO,   \
                                                               const aule_kp::FwdParams p) {              \
-        fwd100::fwd_body<DD, BF, EMU>(&tmQ, &tmK, &tmV, &tmO, p);                                        \
+        fwd100v3::fwd_body<DD, BF, EMU>(&tmQ, &tmK, &tmV, &tmO, p);                                        \
     }
 
-#ifndef AULE_FWD_EMU4
-#define AULE_FWD_EMU4 0          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
-#endif
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4)
-// tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v))
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1)
+// v3 of the forward kernel (S/P aliased, per-tile S buffers), kept as an A/B baseline for v4.
+AULE_FWD100(aule_fwd_sm100_bf16_d128_v3, 128, true, 0)
