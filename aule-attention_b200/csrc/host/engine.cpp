@@ -101,7 +101,7 @@ std::string Engine::load_device(int ordinal) {
                                               (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem d128)");
     }
     static const char* kVariants[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
-                                       "aule_fwd_sm100_bf16_d128_v3", nullptr};
+                                       "aule_fwd_sm100_bf16_d128_v3", "aule_fwd_sm100_bf16_d128_e2"};
     for (int v = 0; v < 4 && e.empty(); ++v) {
         if (!kVariants[v]) continue;
         e = get(&d.fwd_sm100_var[v], kVariants[v]);
@@ -214,8 +214,12 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         FwdParams p;
         p.lse = (float*)lse;
         p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk;
-        p.num_q_super = (s.Sq + 255) / 256;
-        const uint64_t tiles = (uint64_t)p.num_q_super * s.Hq * s.B;
+        // GQA/MQA groups with an even number of q-heads: a work item pairs two q-heads of one KV head
+        // (equal trip counts, shared K/V tiles); otherwise 256 rows of one head.
+        const bool v3 = path_ == kVariantBase + 2;
+        p.pair_heads = (!v3 && (s.Hq / s.Hkv) % 2 == 0 && pair_heads_enabled_) ? 1 : 0;
+        p.num_q_super = p.pair_heads ? (s.Sq + 127) / 128 : (s.Sq + 255) / 256;
+        const uint64_t tiles = (uint64_t)p.num_q_super * (p.pair_heads ? s.Hq / 2 : s.Hq) * s.B;
         if (tiles > 0xffffffffull) return "problem too large (work-item count exceeds 2^32)";
         p.num_tiles = (uint32_t)tiles;
         p.scale = scale;
@@ -231,7 +235,7 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         unsigned smem_use = smem;
         if (path_ >= kVariantBase && path_ < kVariantBase + 4 && dtype == kBF16 && d128 && d.fwd_sm100_var[path_ - kVariantBase]) {
             static const char* kNames[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
-                                            "aule_fwd_sm100_bf16_d128_v3", ""};
+                                            "aule_fwd_sm100_bf16_d128_v3", "aule_fwd_sm100_bf16_d128_e2"};
             fn = d.fwd_sm100_var[path_ - kVariantBase];
             snprintf(name, sizeof(name), "%s", kNames[path_ - kVariantBase]);
             if (path_ - kVariantBase == 2) smem_use = aule_kp::FwdCfgV3<128>::SMEM_BYTES;

@@ -91,7 +91,8 @@ public:
     std::string copy_d2h(int dev, void* dst, CUdeviceptr src, size_t bytes);
     std::string synchronize(int dev);
 
-    void set_kernel_path(int32_t p) { path_ = p; }
+    // path: 0 auto, 1 force CUDA-core kernels, 16+v tuning variant v; bit 8 (256) disables head pairing.
+    void set_kernel_path(int32_t p) { pair_heads_enabled_ = !(p & 256); path_ = p & 255; }
     uint64_t launch_count() const { return launches_; }
     const char* last_kernel() const { return last_kernel_.c_str(); }
 
@@ -107,6 +108,7 @@ private:
     std::vector<Device> devices_;
     bool ready_ = false;
     int32_t path_ = kAuto;
+    bool pair_heads_enabled_ = true;
     uint64_t launches_ = 0;
     std::string last_kernel_ = "none";
 };

@@ -61,20 +61,38 @@ enum : int {
 
 struct Work {
     uint32_t bh, bkv, row0, n0, n1;
+    uint32_t dbh, drow;          // tile t covers q-head (bh + t*dbh), rows [row0 + t*drow, +128)
 };
 
+// Work items, heaviest first under causal masking.
+//  pair_heads: 128 query rows x the two q-heads (2h, 2h+1) of one KV group -> both tiles walk the same
+//              K/V blocks and have EQUAL trip counts (no idle slot for tile 0), K/V tiles shared.
+//  otherwise : 256 query rows of one q-head (tile 1 needs one more block than tile 0 under causal).
 __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     Work t;
-    const uint32_t per = p.Hq * p.B;
-    const uint32_t qrev = w / per;
-    t.bh = w - qrev * per;
-    const uint32_t qs = p.causal ? (p.num_q_super - 1 - qrev) : qrev;   // heaviest first under causal
-    const uint32_t hq = t.bh % p.Hq, b = t.bh / p.Hq;
-    t.bkv = b * p.Hkv + hq / (p.Hq / p.Hkv);
-    t.row0 = qs * 256;
     const uint32_t nkb = (p.Sk + 127) / 128;
-    t.n0 = p.causal ? min(nkb, t.row0 / 128 + 1) : nkb;    // KV blocks tile 0 needs (diagonal included)
-    t.n1 = p.causal ? min(nkb, t.row0 / 128 + 2) : nkb;    // n0 <= n1 always
+    if (p.pair_heads) {
+        const uint32_t hp_n = p.Hq / 2, per = hp_n * p.B;
+        const uint32_t qrev = w / per, rem = w - qrev * per;
+        const uint32_t hp = rem % hp_n, b = rem / hp_n;
+        const uint32_t qb = p.causal ? (p.num_q_super - 1 - qrev) : qrev;
+        t.bh = b * p.Hq + 2 * hp;
+        t.bkv = b * p.Hkv + (2 * hp) / (p.Hq / p.Hkv);
+        t.row0 = qb * 128;
+        t.n0 = t.n1 = p.causal ? min(nkb, qb + 1) : nkb;
+        t.dbh = 1; t.drow = 0;
+    } else {
+        const uint32_t per = p.Hq * p.B;
+        const uint32_t qrev = w / per;
+        t.bh = w - qrev * per;
+        const uint32_t qs = p.causal ? (p.num_q_super - 1 - qrev) : qrev;
+        const uint32_t hq = t.bh % p.Hq, b = t.bh / p.Hq;
+        t.bkv = b * p.Hkv + hq / (p.Hq / p.Hkv);
+        t.row0 = qs * 256;
+        t.n0 = p.causal ? min(nkb, t.row0 / 128 + 1) : nkb;    // KV blocks tile 0 needs (diagonal included)
+        t.n1 = p.causal ? min(nkb, t.row0 / 128 + 2) : nkb;    // n0 <= n1 always
+        t.dbh = 0; t.drow = 128;
+    }
     return t;
 }
 
@@ -154,7 +172,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             const uint32_t n = t ? wk.n1 : wk.n0;
-            const uint32_t trow0 = wk.row0 + t * 128;
+            const uint32_t trow0 = wk.row0 + t * wk.drow;
             const uint32_t grow = trow0 + r;                        // global query row
             float m_used = -INFINITY, l = 0.f;
             for (uint32_t j = 0; j < n; ++j, ++g) {
@@ -209,7 +227,9 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         }
                     }
                 }
-                const float neg_ms = (m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2;
+                // bf16: P is packed by TRUNCATION (one PRMT instead of the quarter-rate F2FP); the exponent carries
+                // +log2(1+2^-9) so that the truncated values are unbiased, and l is corrected by the same factor.
+                const float neg_ms = ((m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2) + (BF16 ? 0.0028150156f : 0.f);
                 // P = exp2(s*scale_log2 - m*scale_log2), two values per instruction (f32x2). EMU4 of every 4
                 // pairs may take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
@@ -228,7 +248,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             e.y = ex2(x.y);
                         }
                         if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
-                        pk[c & 1][i] = pack2<BF16>(e.x, e.y);
+                        pk[c & 1][i] = BF16 ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<false>(e.x, e.y);
                     }
                     if (c == 1) {
                         // P_t is still being read by PV_t of the previous block until pv_done: the first
@@ -254,7 +274,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             }
             // hand the row statistics to the epilogue warps
             mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
-            sStat[t * 128 + r] = l;
+            sStat[t * 128 + r] = BF16 ? l * (1.f / 1.001953125f) : l;   // undo the 1+2^-9 bias carried by the exponents
             sStat[256 + t * 128 + r] = m_used;
             mbar_arrive(bar(B_STFULL + t));
         }
@@ -306,12 +326,12 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 if (issuer) {
 #pragma unroll
                     for (int c = 0; c < C::CHUNKS; ++c)
-                        tma_store_3d(tmO, sO + c * C::CHUNK_BYTES, c * 64, (int32_t)(wk.row0 + t * 128), (int32_t)wk.bh);
+                        tma_store_3d(tmO, sO + c * C::CHUNK_BYTES, c * 64, (int32_t)(wk.row0 + t * wk.drow), (int32_t)(wk.bh + t * wk.dbh));
                     tma_store_commit();
                 }
-                const uint32_t grow = wk.row0 + t * 128 + r;
+                const uint32_t grow = wk.row0 + t * wk.drow + r;
                 if (p.lse != nullptr && grow < p.Sq)
-                    p.lse[(size_t)wk.bh * p.Sq + grow] = m * p.scale + __logf(l);   // LSE = m + ln(l)
+                    p.lse[(size_t)(wk.bh + t * wk.dbh) * p.Sq + grow] = m * p.scale + __logf(l);   // LSE = m + ln(l)
             }
         }
         if (issuer) tma_store_wait_all<0>();
@@ -436,7 +456,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 #pragma unroll
                         for (int c = 0; c < C::CHUNKS; ++c)
                             tma_load_3d(sb + C::OFF_Q + t * C::TILE_BYTES + c * C::CHUNK_BYTES, tmQ, full, c * 64,
-                                        (int32_t)(wk.row0 + t * 128), (int32_t)wk.bh);
+                                        (int32_t)(wk.row0 + t * wk.drow), (int32_t)(wk.bh + t * wk.dbh));
                     }
                     if (wk.n1 > 1) load_kv(tmK, 1, wk.bkv);         // same order as the MMA thread acquires
                     for (uint32_t j = 0; j < wk.n1; ++j) {
@@ -473,3 +493,4 @@ AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4)
 // tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v))
 AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0)
 AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1)
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 2)

@@ -26,6 +26,8 @@ struct FwdParams {
     float scale;              // softmax scale (natural)
     float scale_log2;         // scale * log2(e)
     int32_t causal;
+    int32_t pair_heads;       // 1: a work item is 128 rows x 2 adjacent q-heads of one KV group (equal trip counts);
+                              // 0: 256 rows of one q-head
 };
 
 // v4 layout: Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
