@@ -113,7 +113,7 @@ struct Ring {
     }
 };
 
-template <int D, bool BF16, int EMU4>
+template <int D, bool BF16, int EMU4, bool TRUNC_PACK>
 __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
                                          const CUtensorMap* tmO, const FwdParams& p) {
     using C = Cfg<D>;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 }
                 // bf16: P is packed by TRUNCATION (one PRMT instead of the quarter-rate F2FP); the exponent carries
                 // +log2(1+2^-9) so that the truncated values are unbiased, and l is corrected by the same factor.
-                const float neg_ms = ((m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2) + (BF16 ? 0.0028150156f : 0.f);
+                const float neg_ms = ((m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2) + ((BF16 && TRUNC_PACK) ? 0.0028150156f : 0.f);
                 // P = exp2(s*scale_log2 - m*scale_log2), two values per instruction (f32x2). EMU4 of every 4
                 // pairs may take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
@@ -248,7 +248,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             e.y = ex2(x.y);
                         }
                         if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
-                        pk[c & 1][i] = BF16 ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<false>(e.x, e.y);
+                        pk[c & 1][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
                     }
                     if (c == 1) {
                         // P_t is still being read by PV_t of the previous block until pv_done: the first
@@ -274,7 +274,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             }
             // hand the row statistics to the epilogue warps
             mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
-            sStat[t * 128 + r] = BF16 ? l * (1.f / 1.001953125f) : l;   // undo the 1+2^-9 bias carried by the exponents
+            sStat[t * 128 + r] = (BF16 && TRUNC_PACK) ? l * (1.f / 1.001953125f) : l;   // undo the 1+2^-9 bias carried by the exponents
             sStat[256 + t * 128 + r] = m_used;
             mbar_arrive(bar(B_STFULL + t));
         }
@@ -474,23 +474,26 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 
 }  // namespace fwd100
 
-#define AULE_FWD100(NAME, DD, BF, EMU)                                                                  \
+#define AULE_FWD100(NAME, DD, BF, EMU, TP)                                                              \
     extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
                                                               const __grid_constant__ CUtensorMap tmO,   \
                                                               const aule_kp::FwdParams p) {              \
-        fwd100::fwd_body<DD, BF, EMU>(&tmQ, &tmK, &tmV, &tmO, p);                                        \
+        fwd100::fwd_body<DD, BF, EMU, TP>(&tmQ, &tmK, &tmV, &tmO, p);                                    \
     }
 
 #ifndef AULE_FWD_EMU4
 #define AULE_FWD_EMU4 0          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
 #endif
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4)
+#ifndef AULE_FWD_TRUNC
+#define AULE_FWD_TRUNC true      // bf16 P packed by bias-compensated truncation (PRMT) instead of F2FP
+#endif
+AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC)
+AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC)
+AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false)
+AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false)
 // tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v))
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 2)
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0, false)     // MUFU only, F2FP (RN) packing
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1, true)
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, false)     // 25% polynomial, F2FP packing
