@@ -484,7 +484,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     }
 
 #ifndef AULE_FWD_EMU4
-#define AULE_FWD_EMU4 0          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
+#define AULE_FWD_EMU4 1          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
 #endif
 #ifndef AULE_FWD_TRUNC
 #define AULE_FWD_TRUNC true      // bf16 P packed by bias-compensated truncation (PRMT) instead of F2FP
