@@ -14,6 +14,8 @@ extern "C" const unsigned char aule_cubin_end[];
 
 namespace aule {
 
+using aule_kp::BwdCfg;
+using aule_kp::BwdParams;
 using aule_kp::FwdCfg;
 using aule_kp::FwdParams;
 using aule_kp::SimtParams;
@@ -99,6 +101,18 @@ std::string Engine::load_device(int ordinal) {
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.fwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem d128)");
+    }
+    for (int t = 1; t < 3 && e.empty(); ++t) {
+        e = get(&d.bwd_sm100[t][0], std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + "_d64");
+        if (e.empty()) e = get(&d.bwd_sm100[t][1], std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty()) e = get(&d.bwd_delta[t], std::string("aule_bwd_delta_") + kDtypeSuffix[t]);
+        if (e.empty()) e = get(&d.bwd_cvt[t], std::string("aule_bwd_dq_convert_") + kDtypeSuffix[t]);
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)BwdCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d64)");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)BwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d128)");
     }
     static const char* kVariants[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
                                        "aule_fwd_sm100_bf16_d128_v3", "aule_fwd_sm100_bf16_d128_e2"};
@@ -272,6 +286,55 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     CUdeviceptr delta = 0;
     const size_t dbytes = (size_t)s.B * s.Hq * s.Sq * sizeof(float);
     if (!(e = check(drv_.cuMemAllocAsync(&delta, dbytes, stream), "cuMemAllocAsync(delta)")).empty()) return e;
+
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && path_ != kForceCudaCore &&
+                    ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0;
+    if (tc) {
+        // Tensor-core backward: Delta pre-pass, fused dK/dV/dQ kernel (dQ reduced in an fp32 workspace), convert.
+        CUdeviceptr ws = 0;
+        const uint64_t nq = (uint64_t)s.B * s.Hq * s.Sq * s.D;
+        e = check(drv_.cuMemAllocAsync(&ws, nq * sizeof(float), stream), "cuMemAllocAsync(dq workspace)");
+        if (e.empty()) e = check(drv_.cuMemsetD8Async(ws, 0, nq * sizeof(float), stream), "cuMemsetD8Async(dq workspace)");
+        char name[64];
+        if (e.empty()) {
+            uint64_t rows = (uint64_t)s.B * s.Hq * s.Sq;
+            uint32_t D = s.D;
+            void* params[] = {&o, &d_o, &delta, &rows, &D};
+            snprintf(name, sizeof(name), "aule_bwd_delta_%s", kDtypeSuffix[dtype]);
+            e = launch(d, d.bwd_delta[dtype], name, (unsigned)((rows + 7) / 8), 1, 1, 256, 0, stream, params);
+        }
+        if (e.empty()) {
+            CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+            e = make_tmap(&tmQ, dtype, q, (uint64_t)s.B * s.Hq, s.Sq, s.D);
+            if (e.empty()) e = make_tmap(&tmdO, dtype, d_o, (uint64_t)s.B * s.Hq, s.Sq, s.D);
+            if (e.empty()) e = make_tmap(&tmK, dtype, k, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
+            if (e.empty()) e = make_tmap(&tmV, dtype, v, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
+            if (e.empty()) e = make_tmap(&tmdK, dtype, dk, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
+            if (e.empty()) e = make_tmap(&tmdV, dtype, dv, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
+            BwdParams bp;
+            bp.dq_ws = (float*)ws; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
+            bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk;
+            bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
+            const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
+            if (e.empty() && ctas > 0x7fffffffull) e = "problem too large (backward grid exceeds 2^31 CTAs)";
+            if (e.empty()) {
+                const bool d128 = s.D == 128;
+                void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
+                snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+                e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, 128,
+                           d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
+            }
+        }
+        if (e.empty()) {
+            uint64_t n = nq;
+            void* params[] = {&ws, &dq, &n, &scale};
+            snprintf(name, sizeof(name), "aule_bwd_dq_convert_%s", kDtypeSuffix[dtype]);
+            e = launch(d, d.bwd_cvt[dtype], name, (unsigned)std::min<uint64_t>((nq / 2 + 255) / 256, 148 * 16), 1, 1, 256, 0, stream, params);
+        }
+        if (ws) drv_.cuMemFreeAsync(ws, stream);
+        drv_.cuMemFreeAsync(delta, stream);
+        return e;
+    }
     SimtParams p;
     memset(&p, 0, sizeof(p));
     p.q = (const void*)q; p.k = (const void*)k; p.v = (const void*)v; p.o = (void*)o;

@@ -44,6 +44,9 @@ struct Device {
     CUfunction bwd_dkv_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     CUfunction fwd_sm100_var[4] = {nullptr, nullptr, nullptr, nullptr};   // bf16 d128 tuning variants (_e0.._e3)
+    CUfunction bwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
+    CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
+    CUfunction bwd_cvt[3] = {nullptr, nullptr, nullptr};
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;

@@ -194,3 +194,64 @@ def test_sdpa_shim_and_install(aule):
     finally:
         aule.uninstall()
     assert (out.float() - ref.float()).abs().max().item() <= 2e-2
+
+
+BWD_SHAPES = [
+    # B, Hq, Hkv, Sq, Sk, D, causal
+    (1, 2, 2, 128, 128, 64, True),
+    (1, 2, 2, 128, 128, 128, False),
+    (2, 4, 4, 256, 256, 64, True),
+    (1, 8, 2, 384, 384, 128, True),     # GQA 4:1: dK/dV summed over the group inside the CTA
+    (1, 4, 1, 200, 200, 64, True),      # MQA, ragged tail
+    (1, 2, 2, 100, 333, 128, False),    # cross attention, ragged Sk
+    (1, 2, 1, 300, 129, 128, True),     # Sq > Sk causal
+    (1, 2, 2, 64, 300, 64, True),       # keys beyond every query: dK = dV = 0 there
+    (2, 16, 16, 1024, 1024, 64, True),  # BASELINE.json configs[4]
+]
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,D,causal", BWD_SHAPES)
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_tensor_core_backward_vs_oracle(aule, B, Hq, Hkv, Sq, Sk, D, causal, dtype):
+    """dQ/dK/dV of the tcgen05 backward vs the analytic fp64 oracle on the rounded inputs;
+    gate 1e-2 relative to scale (python/tests/test_triton.py:92-94 uses 1e-2/1e-2)."""
+    import torch
+    from aule import ffi
+    if (B, Sq) == (2, 1024) and dtype == "f16":
+        pytest.skip("one dtype is enough at the largest shape")
+    td = {"bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    q, k, v = ref_inputs(B, Hq, Sq, D, Hkv=Hkv, Sk=Sk)
+    do = np.random.RandomState(1).randn(B, Hq, Sq, D).astype(np.float32)
+    tq, tk, tv = (torch.from_numpy(x).cuda().to(td).requires_grad_() for x in (q, k, v))
+    tdo = torch.from_numpy(do).cuda().to(td)
+    out = aule.flash_attention(tq, tk, tv, causal=causal)
+    out.backward(tdo)
+    torch.cuda.synchronize()
+    assert ffi.load_library().aule_last_kernel().decode() == f"aule_bwd_dq_convert_{dtype}"
+    rq, rk, rv, rdo = (t.detach().float().cpu().numpy() for t in (tq, tk, tv, tdo))
+    dq, dk, dv, _, _ = orc.attention_bwd_ref(rq, rk, rv, rdo, causal=causal)
+    for name, g, e in (("dq", tq.grad, dq), ("dk", tk.grad, dk), ("dv", tv.grad, dv)):
+        got = g.float().cpu().numpy()
+        assert np.isfinite(got).all(), name
+        assert orc.rel_err_to_scale(got, e) <= 1e-2, (name, orc.rel_err_to_scale(got, e))
+
+
+def test_tensor_core_backward_agrees_with_cuda_core_backward(aule):
+    import torch
+    from aule import ffi
+    lib = ffi.load_library()
+    torch.manual_seed(3)
+    q, k, v = (torch.randn(2, 8, 512, 128, device="cuda").to(torch.bfloat16) for _ in range(3))
+    k, v = k[:, :2].contiguous(), v[:, :2].contiguous()
+    do = torch.randn(2, 8, 512, 128, device="cuda").to(torch.bfloat16)
+    grads = []
+    for path in (0, 1):
+        lib.aule_set_kernel_path(path)
+        try:
+            tq, tk, tv = (t.clone().requires_grad_() for t in (q, k, v))
+            aule.flash_attention(tq, tk, tv, causal=True).backward(do)
+            grads.append((tq.grad.float(), tk.grad.float(), tv.grad.float()))
+        finally:
+            lib.aule_set_kernel_path(0)
+    for a, b in zip(*grads):
+        assert (a - b).abs().max().item() / b.abs().max().item() <= 1e-2
