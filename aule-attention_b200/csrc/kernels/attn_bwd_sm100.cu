@@ -186,24 +186,21 @@ __device__ __forceinline__ void bwd_body(const CUtensorMap* tmQ, const CUtensorM
         if (threadIdx.x == 0 && step + 1 < nsteps) load_qdo(step + 1);   // Q/dO buffers are free again
 
         // ---- dQ partial (TMEM cols [0,D)) -> fp32 workspace, 16-byte vector reductions
-        if (row_ok) {
-            float* dst = p.dq_ws + (stat_off + row) * D;
+        {
+            // tcgen05.ld is warp-collective (.sync.aligned): every lane executes it, only the reductions are
+            // predicated on the row being in range (ragged last query block).
+            float* dst = p.dq_ws + (stat_off + (row_ok ? row : 0)) * D;
 #pragma unroll 1
             for (int c = 0; c < D / 32; ++c) {
                 uint32_t q[32];
                 tmem_ld32(tmem + lane_addr + COL_S + c * 32, q);
                 tmem_wait_ld();
+                if (row_ok) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + e), "f"(__uint_as_float(q[e])),
-                                 "f"(__uint_as_float(q[e + 1])), "f"(__uint_as_float(q[e + 2])), "f"(__uint_as_float(q[e + 3])) : "memory");
-            }
-        } else {
-#pragma unroll 1
-            for (int c = 0; c < D / 32; ++c) {                        // keep the warp-collective loads converged
-                uint32_t q[32];
-                tmem_ld32(tmem + lane_addr + COL_S + c * 32, q);
-                tmem_wait_ld();
+                    for (int e = 0; e < 32; e += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + e), "f"(__uint_as_float(q[e])),
+                                     "f"(__uint_as_float(q[e + 1])), "f"(__uint_as_float(q[e + 2])), "f"(__uint_as_float(q[e + 3])) : "memory");
+                }
             }
         }
         tc_fence_before();
