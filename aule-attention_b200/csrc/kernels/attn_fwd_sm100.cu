@@ -113,7 +113,7 @@ struct Ring {
     }
 };
 
-template <int D, bool BF16, int EMU4, bool TRUNC_PACK>
+template <int D, bool BF16, int EMU4, bool TRUNC_PACK, uint32_t HOT_HINT>
 __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
                                          const CUtensorMap* tmO, const FwdParams& p) {
     using C = Cfg<D>;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             const uint32_t grow = trow0 + r;                        // global query row
             float m_used = -INFINITY, l = 0.f;
             for (uint32_t j = 0; j < n; ++j, ++g) {
-                mbar_wait(bar(B_SFULL + t), g & 1);
+                mbar_wait<HOT_HINT>(bar(B_SFULL + t), g & 1);
                 tc_fence_after();
                 uint32_t s[4][32];
 #pragma unroll
@@ -185,13 +185,22 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 tc_fence_before();
                 mbar_arrive(bar(B_SFREE));                          // S may be overwritten by the next Q K^T
                 const bool need_mask = (p.causal && j * 128 + 127 > trow0) || ((j + 1) * 128 > p.Sk);
-                if (need_mask) {
+                if (need_mask) {                                    // diagonal / ragged-tail blocks only: kept rolled (I-cache)
                     const uint32_t lim = p.causal ? min(grow, p.Sk - 1) : p.Sk - 1;   // last visible key
+                    const int32_t thr = (int32_t)lim - (int32_t)(j * 128);            // columns > thr are masked (a suffix)
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        if (thr >= c * 32 + 31) continue;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (j * 128 + c * 32 + i > lim) s[c][i] = 0xff800000u;        // -inf
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t neg = (c * 32 + i > thr) ? 0xff800000u : 0u;   // -inf
+                            // dynamic c: select the chunk without dynamic register indexing
+                            if (c == 0) s[0][i] = neg ? neg : s[0][i];
+                            else if (c == 1) s[1][i] = neg ? neg : s[1][i];
+                            else if (c == 2) s[2][i] = neg ? neg : s[2][i];
+                            else s[3][i] = neg ? neg : s[3][i];
+                        }
+                    }
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -213,7 +222,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     l *= alpha;
                     if (grow_max) m_used = m_new;
                     if (j > 0) {
-                        mbar_wait(bar(B_PVDONE + t), (g - 1) & 1);   // PV_t(j-1) complete: O_t is stable
+                        mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);   // PV_t(j-1) complete: O_t is stable
                         pv_waited = true;
                         tc_fence_after();
 #pragma unroll 1
@@ -253,7 +262,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     if (c == 1) {
                         // P_t is still being read by PV_t of the previous block until pv_done: the first
                         // two chunks are computed under that MMA and stored once it has finished.
-                        if (g > 0 && !pv_waited) mbar_wait(bar(B_PVDONE + t), (g - 1) & 1);
+                        if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
                         tc_fence_after();
                         tmem_st16(tP, pk[0]);
                         tmem_st16(tP + 16, pk[1]);
@@ -351,12 +360,12 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
                 auto acquire = [&]() -> uint32_t {                  // wait for the next tile of the load order
                     const uint32_t st = ring.stage;
-                    mbar_wait(bar(B_KVFULL + st), ring.phase);
+                    mbar_wait<HOT_HINT>(bar(B_KVFULL + st), ring.phase);
                     ring.advance<NS>();
                     return st;
                 };
                 auto issue_qk = [&](uint32_t t, uint32_t kstage) {  // S = Q_t K^T (waits until S has been drained)
-                    if (nqk > 0) mbar_wait(bar(B_SFREE), (nqk - 1) & 1);
+                    if (nqk > 0) mbar_wait<HOT_HINT>(bar(B_SFREE), (nqk - 1) & 1);
                     ++nqk;
                     tc_fence_after();
                     const uint32_t a_lo = HI_K_LO | ((sb + C::OFF_Q + t * C::TILE_BYTES) >> 4);
@@ -374,13 +383,13 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     const uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
                     const uint32_t a = tmem + (t ? C::COL_P1 : C::COL_P0);
                     const uint32_t d = tmem + (t ? C::COL_O1 : C::COL_O0);
-                    mbar_wait(bar(B_PFULL + t), gpv & 1);
+                    mbar_wait<HOT_HINT>(bar(B_PFULL + t), gpv & 1);
                     if (first) mbar_wait(bar(B_OEMPTY + t), (it & 1) ^ 1);   // epilogue drained the previous O_t
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 6; ++kk)
                         mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (!first || kk > 0) ? 1u : 0u);
-                    mbar_wait(bar(B_PFULLB + t), gpv & 1);
+                    mbar_wait<HOT_HINT>(bar(B_PFULLB + t), gpv & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 6; kk < 8; ++kk)
@@ -474,13 +483,13 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 
 }  // namespace fwd100
 
-#define AULE_FWD100(NAME, DD, BF, EMU, TP)                                                              \
+#define AULE_FWD100(NAME, DD, BF, EMU, TP, HINT)                                                        \
     extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
                                                               const __grid_constant__ CUtensorMap tmO,   \
                                                               const aule_kp::FwdParams p) {              \
-        fwd100::fwd_body<DD, BF, EMU, TP>(&tmQ, &tmK, &tmV, &tmO, p);                                    \
+        fwd100::fwd_body<DD, BF, EMU, TP, HINT>(&tmQ, &tmK, &tmV, &tmO, p);                              \
     }
 
 #ifndef AULE_FWD_EMU4
@@ -489,11 +498,14 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 #ifndef AULE_FWD_TRUNC
 #define AULE_FWD_TRUNC true      // bf16 P packed by bias-compensated truncation (PRMT) instead of F2FP
 #endif
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false)
+#ifndef AULE_FWD_HINT
+#define AULE_FWD_HINT 1000000u   // suspend hint (ns) of the waits on the softmax <-> MMA critical path
+#endif
+AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
+AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
+AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false, AULE_FWD_HINT)
+AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false, AULE_FWD_HINT)
 // tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v))
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0, false)     // MUFU only, F2FP (RN) packing
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1, true)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, false)     // 25% polynomial, F2FP packing
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 1, true, 0u)         // plain try_wait on the critical path
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1, true, 2000u)      // 2 us hint
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, true, 200u)       // 0.2 us hint

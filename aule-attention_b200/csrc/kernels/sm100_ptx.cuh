@@ -40,30 +40,44 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// HINT_NS: suspend-time hint of mbarrier.try_wait (the thread may sleep up to that long before re-checking;
+// a completing phase wakes it).  0 = plain try_wait (hardware default time limit).
+template <uint32_t HINT_NS = 1000000u>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000000u)     // suspend-time hint (ns): idle roles sleep instead of spinning
-        : "memory");
+    if constexpr (HINT_NS == 0) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(HINT_NS)
+            : "memory");
+    }
     return ok != 0;
 }
 // Wait until the phase with the given parity has completed.
+template <uint32_t HINT_NS = 1000000u>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if AULE_WATCHDOG
-    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait<HINT_NS>(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait<HINT_NS>(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {      // ~2 s: a pipeline bug, not a slow kernel
             printf("[aule] mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
             __trap();
         }
     }
 #else
-    while (!mbar_try_wait(bar, parity)) {}
+    while (!mbar_try_wait<HINT_NS>(bar, parity)) {}
 #endif
 }
 
