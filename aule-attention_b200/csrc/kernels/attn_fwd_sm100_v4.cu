@@ -6,59 +6,56 @@
 // Semantics kept: O = softmax(scale*QK^T + mask) V; top-left causal mask (j <= i,
 // triton_flash.py:187); GQA kv_head = q_head / (Hq/Hkv) (:95-96); LSE = m + ln(l) (:232).
 //
-// One persistent CTA per SM (768 threads) looping over work items (two 128-row query tiles that share their
-// K/V blocks), heaviest first, dealt in snake order:                                      (kernel v5)
+// One persistent CTA per SM (512 threads) looping over work items (256 query rows = two
+// 128-row tiles of one (batch, q-head)), heaviest first, dealt in snake order:
 //
-//   warps  0-3 / 4-7    softmax, tile 0, keys [0,64) / [64,128) of each block
-//   warps  8-11 / 12-15 softmax, tile 1, keys [0,64) / [64,128)
-//          thread == (query row, column half): S TMEM -> registers, exp2, P -> TMEM.  Splitting the columns
-//          puts FOUR softmax warps on every SM sub-partition (v4 had two, each latency-bound at ~0.25 IPC with
-//          the MUFU pipe only 50 % busy); the row maximum is exchanged through shared memory, the row sums stay
-//          per half and are added once per work item.
-//   warps 16-19         epilogue (O: TMEM -> regs -> 1/l -> global, 32 B per thread per store; LSE)
-//   warp  20            MMA issuer (one elected thread issues every tcgen05.mma)
-//   warp  21            TMA producer (one elected thread issues every bulk tensor load)
-//   warp  22            TMEM allocator
+//   warps 0-3   softmax, tile 0   (thread == query row: S TMEM -> registers, exp2, P -> TMEM)
+//   warps 4-7   softmax, tile 1
+//   warps 8-11  epilogue          (O: TMEM -> regs -> 1/l -> SMEM -> TMA store; LSE)
+//   warp  12    MMA issuer        (one elected thread issues every tcgen05.mma)
+//   warp  13    TMA producer      (one elected thread issues every bulk tensor load)
+//   warp  14    TMEM allocator
 //
 // TMEM (512 columns): S [0,128) shared by both tiles | P0 [128,192) | P1 [192,256) |
 //                     O0 [256,256+D) | O1 [256+D,256+2D).
-// S only lives from the end of Q K^T until the softmax warps have copied it to registers, so ONE S buffer
-// serves both tiles and P gets columns of its own: the next Q K^T of a tile is issued as soon as the OTHER
-// tile's softmax has drained S and runs under this tile's exp phase.
+// S only lives from the end of Q K^T until the softmax warps have copied it to registers
+// (~150 cycles), so ONE S buffer serves both tiles and P gets columns of its own.  That removes the
+// S/P aliasing of v3 and with it the serial chain  softmax(j) -> P V -> Q K^T(j+1) -> softmax(j+1):
+// the next Q K^T of a tile is issued as soon as the OTHER tile's softmax has drained S, and runs
+// under this tile's exp phase, so the softmax warps (the MUFU-bound stage) never wait for it.
 // Steady-state issue order of the MMA thread (all waits blocking, order == readiness order):
 //     PV_0(j)  QK_1(j+1)  PV_1(j)  QK_0(j+2)  PV_0(j+1)  QK_1(j+2)  ...
-// PV_t(j) is issued in two halves: k-steps 0..3 once the half-0 warps have stored keys 0..63 of P (and the
-// half-1 warps have finished any rescale of their O columns), k-steps 4..7 once half 1 has stored its keys.
-// Hazards: P_t is rewritten for block j+1 only after pv_done[t] (commit after PV_t(j)); the rare in-place O_t
-// rescale waits for the same barrier; S is handed over through s_free (256 arrivals after the tcgen05.ld).
+// Hazards: P_t is rewritten for block j+1 only after pv_done[t] (commit after PV_t(j)); the rare
+// in-place O_t rescale waits for the same barrier; S is handed over through s_free (128 arrivals
+// after the tcgen05.ld of S completes).
 //
-// SMEM (D=128): Q 2x32 KB | K/V ring 4x32 KB (load order K0 K1 V0 K2 V1 K3 ...) | row-max exchange 4 KB |
-// row statistics 3 KB | mbarriers.  All operand tiles are [128 rows][64 elements] 128B-swizzled sub-tiles
-// (TMA box 64x128): the K-major canonical UMMA layout for Q/K and the MN-major one for V.
+// SMEM (D=128): Q 2x32 KB | K/V ring 4x32 KB (load order K0 K1 V0 K2 V1 K3 ...) | O staging 32 KB |
+// row statistics 2 KB | mbarriers.  All operand tiles are [128 rows][64 elements] 128B-swizzled
+// sub-tiles (TMA box 64x128): the K-major canonical UMMA layout for Q/K and the MN-major one for V.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "sm100_ptx.cuh"
 #include "kernel_params.h"
 
-namespace fwd100 {
+namespace fwd100v4 {
 using namespace sm100;
 using aule_kp::FwdParams;
-template <int D> using Cfg = aule_kp::FwdCfg<D>;
+template <int D> using Cfg = aule_kp::FwdCfgV4<D>;
 
 // barrier indices (pairs are indexed by tile)
 enum : int {
     B_QFULL = 0,     // TMA -> MMA: Q_t landed
     B_QEMPTY = 2,    // MMA -> TMA: last QK_t of the work item done (commit)
     B_SFULL = 4,     // MMA -> softmax t: S holds Q_t K^T (commit)
-    B_PFULL = 6,     // softmax t -> MMA: P_t keys 0..63 written (half 0) + O columns of half 1 stable (256 arrivals)
-    B_PFULLB = 8,    // softmax t -> MMA: P_t keys 64..127 written (half 1, 128 arrivals)
+    B_PFULL = 6,     // softmax t -> MMA: P_t columns [0,48) written (keys 0..95)
+    B_PFULLB = 8,    // softmax t -> MMA: P_t columns [48,64) written (keys 96..127)
     B_PVDONE = 10,   // MMA -> softmax t: PV_t(j) complete (commit): P_t / O_t may be touched
     B_OFULL = 12,    // MMA -> epilogue: last PV_t of the work item done (commit)
     B_OEMPTY = 14,   // epilogue -> MMA: O_t drained from TMEM
     B_STFULL = 16,   // softmax t -> epilogue: row statistics written
     B_STEMPTY = 18,  // epilogue -> softmax t: row statistics consumed
-    B_SFREE = 20,    // softmax (either tile, both halves: 256 arrivals) -> MMA: S copied to registers
+    B_SFREE = 20,    // softmax (either tile) -> MMA: S copied to registers
     B_KVFULL = 21    // + NS: kv_empty
 };
 
@@ -125,26 +122,25 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     const uint32_t sb = smem_u32(smem);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int i) -> uint32_t { return sb + C::OFF_BAR + 8u * i; };
-    float* sStat = reinterpret_cast<float*>(smem + C::OFF_STAT);          // l[tile][half][128] | m[tile][128]
-    float* sXmax = reinterpret_cast<float*>(smem + C::OFF_XMAX);          // [parity][tile][half][128]
+    float* sStat = reinterpret_cast<float*>(smem + C::OFF_STAT);          // [l0 | l1 | m0 | m1] x 128
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
 
     if (threadIdx.x == 0 && (sb & 1023u)) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
 
-    if (warp == 21 && lane == 0) {
+    if (warp == 13 && lane == 0) {
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar(B_QFULL + t), 1);     // TMA tx
             mbar_init(bar(B_QEMPTY + t), 1);    // tcgen05.commit
             mbar_init(bar(B_SFULL + t), 1);     // tcgen05.commit
-            mbar_init(bar(B_PFULL + t), 256);   // half 0: P stored; half 1: O columns stable
-            mbar_init(bar(B_PFULLB + t), 128);  // half 1: P stored
+            mbar_init(bar(B_PFULL + t), 128);   // softmax threads
+            mbar_init(bar(B_PFULLB + t), 128);  // softmax threads
             mbar_init(bar(B_PVDONE + t), 1);    // tcgen05.commit
             mbar_init(bar(B_OFULL + t), 1);     // tcgen05.commit
             mbar_init(bar(B_OEMPTY + t), 128);  // epilogue threads
-            mbar_init(bar(B_STFULL + t), 256);  // softmax threads (both halves)
+            mbar_init(bar(B_STFULL + t), 128);  // softmax threads
             mbar_init(bar(B_STEMPTY + t), 128); // epilogue threads
         }
-        mbar_init(bar(B_SFREE), 256);           // softmax threads (both halves) of whichever tile owns S
+        mbar_init(bar(B_SFREE), 128);           // softmax threads of whichever tile owns S
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_KVFULL + s), 1);
             mbar_init(bar(B_KVFULL + NS + s), 1);
@@ -152,7 +148,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmO);
     }
-    if (warp == 22) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    if (warp == 14) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,47 +159,52 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     constexpr uint32_t IDESC_QK = instr_desc_f16(BF16, 128, 128, false);
     constexpr uint32_t IDESC_PV = instr_desc_f16(BF16, 128, D, true);
 
-    if (warp < 16) {
-        // ===================================================== softmax warps (tile t, column half h)
-        reg_inc<104>();
-        const uint32_t t = warp >> 3;                               // tile 0 / 1
-        const uint32_t h = (warp >> 2) & 1;                         // keys [64h, 64h+64) of every block
+    if (warp < 8) {
+        // ===================================================== softmax warps
+        reg_inc<192>();
+        const uint32_t t = warp >> 2;                               // tile 0 / 1
         const uint32_t r = (warp & 3) * 32 + lane;                  // row within the tile == TMEM lane
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem + lane_addr + C::COL_S + 64 * h;
-        const uint32_t tP = tmem + lane_addr + (t ? C::COL_P1 : C::COL_P0) + 32 * h;
-        const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0) + (D / 2) * h;   // this half's O columns
+        const uint32_t tS = tmem + lane_addr + C::COL_S;
+        const uint32_t tP = tmem + lane_addr + (t ? C::COL_P1 : C::COL_P0);
+        const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
         uint32_t g = 0, it = 0;                                     // g: blocks processed so far by this tile
         for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             const uint32_t n = t ? wk.n1 : wk.n0;
             const uint32_t trow0 = wk.row0 + t * wk.drow;
             const uint32_t grow = trow0 + r;                        // global query row
-            float m_used = -INFINITY, l = 0.f;                      // l: this half's partial row sum
+            float m_used = -INFINITY, l = 0.f;
             for (uint32_t j = 0; j < n; ++j, ++g) {
                 mbar_wait<HOT_HINT>(bar(B_SFULL + t), g & 1);
                 tc_fence_after();
-                uint32_t s[2][32];
-                tmem_ld32(tS, s[0]);
-                tmem_ld32(tS + 32, s[1]);
+                uint32_t s[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(bar(B_SFREE));                          // S may be overwritten by the next Q K^T
                 const bool need_mask = (p.causal && j * 128 + 127 > trow0) || ((j + 1) * 128 > p.Sk);
-                if (need_mask) {                                    // diagonal / ragged-tail blocks only
+                if (need_mask) {                                    // diagonal / ragged-tail blocks only: kept rolled (I-cache)
                     const uint32_t lim = p.causal ? min(grow, p.Sk - 1) : p.Sk - 1;   // last visible key
-                    const int32_t thr = (int32_t)lim - (int32_t)(j * 128 + 64 * h);   // local columns > thr are masked
-                    if (thr < 63) {
+                    const int32_t thr = (int32_t)lim - (int32_t)(j * 128);            // columns > thr are masked (a suffix)
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        if (thr >= c * 32 + 31) continue;
 #pragma unroll
-                        for (int c = 0; c < 2; ++c)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i > thr) s[c][i] = 0xff800000u;              // -inf
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t neg = (c * 32 + i > thr) ? 0xff800000u : 0u;   // -inf
+                            // dynamic c: select the chunk without dynamic register indexing
+                            if (c == 0) s[0][i] = neg ? neg : s[0][i];
+                            else if (c == 1) s[1][i] = neg ? neg : s[1][i];
+                            else if (c == 2) s[2][i] = neg ? neg : s[2][i];
+                            else s[3][i] = neg ? neg : s[3][i];
+                        }
                     }
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
@@ -211,13 +212,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
                         mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
                     }
-                // row maximum over all 128 keys: exchange the two halves through shared memory (double-buffered
-                // on the block parity so that a fast thread cannot overwrite a value its partner has not read)
-                const float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                float* xm = sXmax + (g & 1) * 512 + t * 256;
-                xm[h * 128 + r] = pm;
-                named_bar_sync(2 + t, 256);
-                const float m_new = fmaxf(fmaxf(pm, xm[(h ^ 1) * 128 + r]), m_used);
+                const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
                 // Lazy rescale: adopt the new maximum only when it grew by more than 2^8 in the
                 // exp2 domain; otherwise P stays <= 256, harmless in bf16/fp16 and fp32 sums.
                 const bool grow_max = (m_new - m_used) * p.scale_log2 > 8.f;   // m_used = -inf -> true
@@ -231,7 +226,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         pv_waited = true;
                         tc_fence_after();
 #pragma unroll 1
-                        for (int c = 0; c < D / 64; ++c) {          // this half's D/2 columns
+                        for (int c = 0; c < D / 32; ++c) {
                             uint32_t o[32];
                             tmem_ld32(tO + c * 32, o);
                             tmem_wait_ld();
@@ -239,23 +234,18 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                             tmem_st32(tO + c * 32, o);
                         }
-                        tmem_wait_st();
                     }
-                }
-                if (h == 1) {                                       // half 1's O columns are stable: PV k-steps 0..3 may go
-                    tc_fence_before();
-                    mbar_arrive(bar(B_PFULL + t));
                 }
                 // bf16: P is packed by TRUNCATION (one PRMT instead of the quarter-rate F2FP); the exponent carries
                 // +log2(1+2^-9) so that the truncated values are unbiased, and l is corrected by the same factor.
                 const float neg_ms = ((m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2) + ((BF16 && TRUNC_PACK) ? 0.0028150156f : 0.f);
                 // P = exp2(s*scale_log2 - m*scale_log2), two values per instruction (f32x2). EMU4 of every 4
-                // pairs take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
+                // pairs may take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
                 uint32_t pk[2][16];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 4; ++c) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
@@ -267,76 +257,96 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             e.y = ex2(x.y);
                         }
                         if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
-                        pk[c][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
+                        pk[c & 1][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
+                    }
+                    if (c == 1) {
+                        // P_t is still being read by PV_t of the previous block until pv_done: the first
+                        // two chunks are computed under that MMA and stored once it has finished.
+                        if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
+                        tc_fence_after();
+                        tmem_st16(tP, pk[0]);
+                        tmem_st16(tP + 16, pk[1]);
+                    } else if (c == 2) {
+                        tmem_st16(tP + 32, pk[0]);                   // keys 0..95 ready: PV k-steps 0..5 may start
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(bar(B_PFULL + t));
+                    } else if (c == 3) {
+                        tmem_st16(tP + 48, pk[1]);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(bar(B_PFULLB + t));
                     }
                 }
-                // P_t is still being read by PV_t of the previous block until pv_done.
-                if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
-                tc_fence_after();
-                tmem_st16(tP, pk[0]);
-                tmem_st16(tP + 16, pk[1]);
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(bar(h ? B_PFULLB + t : B_PFULL + t));
                 const float2 acc = __fadd2_rn(acc0, acc1);
                 l += acc.x + acc.y;
             }
             // hand the row statistics to the epilogue warps
             mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
-            sStat[(t * 2 + h) * 128 + r] = (BF16 && TRUNC_PACK) ? l * (1.f / 1.001953125f) : l;   // undo the 1+2^-9 bias
-            if (h == 0) sStat[512 + t * 128 + r] = m_used;
+            sStat[t * 128 + r] = (BF16 && TRUNC_PACK) ? l * (1.f / 1.001953125f) : l;   // undo the 1+2^-9 bias carried by the exponents
+            sStat[256 + t * 128 + r] = m_used;
             mbar_arrive(bar(B_STFULL + t));
         }
-    } else if (warp < 20) {
+    } else if (warp < 12) {
         // ===================================================== epilogue warps
-        reg_dec<40>();
+        reg_dec<64>();
         const uint32_t r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
+        const bool issuer = (warp == 8 && lane == 0);
+        const uint32_t sO = sb + C::OFF_O;
         uint32_t it = 0;
         for (uint32_t w; next_work(p, it, w); ++it) {
             const Work wk = decode(p, w);
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
                 mbar_wait(bar(B_STFULL + t), it & 1);
-                const float l = sStat[(t * 2) * 128 + r] + sStat[(t * 2 + 1) * 128 + r];
-                const float m = sStat[512 + t * 128 + r];
+                const float l = sStat[t * 128 + r];
+                const float m = sStat[256 + t * 128 + r];
                 mbar_arrive(bar(B_STEMPTY + t));
                 mbar_wait(bar(B_OFULL + t), it & 1);
                 tc_fence_after();
+                if (issuer) tma_store_wait_read<0>();               // the previous store has finished reading sO
+                named_bar_sync(1, 128);
                 const float inv = 1.f / l;
-                const uint32_t grow = wk.row0 + t * wk.drow + r;
-                const bool row_ok = grow < p.Sq;
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.o) + ((size_t)(wk.bh + t * wk.dbh) * p.Sq + (row_ok ? grow : 0)) * D * 2);
-#pragma unroll 1
-                for (int c = 0; c < D / 16; ++c) {
-                    uint32_t o[16];
-                    tmem_ld16(tO + c * 16, o);
+#pragma unroll
+                for (int c = 0; c < D / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tO + c * 32, o);
                     tmem_wait_ld();
-                    if (c == D / 16 - 1) {                          // O_t fully read: MMA may overwrite it
+                    if (c == D / 32 - 1) {                          // O_t fully read: MMA may overwrite it
                         tc_fence_before();
                         mbar_arrive(bar(B_OEMPTY + t));
                     }
-                    uint4 v0, v1;
-                    v0.x = pack2<BF16>(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-                    v0.y = pack2<BF16>(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-                    v0.z = pack2<BF16>(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-                    v0.w = pack2<BF16>(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-                    v1.x = pack2<BF16>(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-                    v1.y = pack2<BF16>(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-                    v1.z = pack2<BF16>(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-                    v1.w = pack2<BF16>(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-                    if (row_ok) {                                   // 32 contiguous bytes (one sector) per thread
-                        dst[c * 2] = v0;
-                        dst[c * 2 + 1] = v1;
+                    // 32 fp32 -> 32 x 16-bit = 64 B = 4 swizzled 16-byte units of this row
+                    const uint32_t chunk = (c * 32) / 64, unit0 = ((c * 32) % 64) / 8;
+                    const uint32_t rowbase = sO + chunk * C::CHUNK_BYTES + r * 128;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t v0 = pack2<BF16>(__uint_as_float(o[8 * u + 0]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
+                        const uint32_t v1 = pack2<BF16>(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
+                        const uint32_t v2 = pack2<BF16>(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
+                        const uint32_t v3 = pack2<BF16>(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
+                        const uint32_t addr = rowbase + (((unit0 + u) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
                     }
                 }
-                if (p.lse != nullptr && row_ok)
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (issuer) {
+#pragma unroll
+                    for (int c = 0; c < C::CHUNKS; ++c)
+                        tma_store_3d(tmO, sO + c * C::CHUNK_BYTES, c * 64, (int32_t)(wk.row0 + t * wk.drow), (int32_t)(wk.bh + t * wk.dbh));
+                    tma_store_commit();
+                }
+                const uint32_t grow = wk.row0 + t * wk.drow + r;
+                if (p.lse != nullptr && grow < p.Sq)
                     p.lse[(size_t)(wk.bh + t * wk.dbh) * p.Sq + grow] = m * p.scale + __logf(l);   // LSE = m + ln(l)
             }
         }
+        if (issuer) tma_store_wait_all<0>();
     } else {
-        reg_dec<56>();
-        if (warp == 20) {
+        reg_dec<64>();
+        if (warp == 12) {
             // ================================================= MMA issuer
             if (elect_one()) {
                 Ring ring;                                          // next K/V ring slot to acquire
@@ -377,12 +387,12 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     if (first) mbar_wait(bar(B_OEMPTY + t), (it & 1) ^ 1);   // epilogue drained the previous O_t
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
+                    for (int kk = 0; kk < 6; ++kk)
                         mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (!first || kk > 0) ? 1u : 0u);
                     mbar_wait<HOT_HINT>(bar(B_PFULLB + t), gpv & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 4; kk < 8; ++kk)
+                    for (int kk = 6; kk < 8; ++kk)
                         mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, 1u);
                     ++gpv;
                     mma_commit(bar(B_PVDONE + t));
@@ -430,7 +440,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     }
                 }
             }
-        } else if (warp == 21) {
+        } else if (warp == 13) {
             // ================================================= TMA producer
             if (elect_one()) {
                 Ring ring;
@@ -468,34 +478,20 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 22) tmem_dealloc<512>(tmem);
+    if (warp == 14) tmem_dealloc<512>(tmem);
 }
 
-}  // namespace fwd100
+}  // namespace fwd100v4
 
+#undef AULE_FWD100
 #define AULE_FWD100(NAME, DD, BF, EMU, TP, HINT)                                                        \
-    extern "C" __global__ void __launch_bounds__(768, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
+    extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
                                                               const __grid_constant__ CUtensorMap tmO,   \
                                                               const aule_kp::FwdParams p) {              \
-        fwd100::fwd_body<DD, BF, EMU, TP, HINT>(&tmQ, &tmK, &tmV, &tmO, p);                              \
+        fwd100v4::fwd_body<DD, BF, EMU, TP, HINT>(&tmQ, &tmK, &tmV, &tmO, p);                              \
     }
 
-#ifndef AULE_FWD_EMU4
-#define AULE_FWD_EMU4 1          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
-#endif
-#ifndef AULE_FWD_TRUNC
-#define AULE_FWD_TRUNC true      // bf16 P packed by bias-compensated truncation (PRMT) instead of F2FP
-#endif
-#ifndef AULE_FWD_HINT
-#define AULE_FWD_HINT 1000000u   // suspend hint (ns) of the waits on the softmax <-> MMA critical path
-#endif
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false, AULE_FWD_HINT)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false, AULE_FWD_HINT)
-// tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v))
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 1, true, 0u)         // plain try_wait on the critical path
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 1, true, 2000u)      // 2 us hint
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, true, 200u)       // 0.2 us hint
+// v4 of the forward kernel (row-per-thread softmax, 2 softmax warps per SMSP), kept as the A/B baseline for v5.
+AULE_FWD100(aule_fwd_sm100_bf16_d128_v4, 128, true, 1, true, 1000000u)
