@@ -165,7 +165,9 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 
     if (warp < 16) {
         // ===================================================== softmax warps (tile t, column half h)
-        reg_inc<104>();
+        // setmaxnreg moves registers inside the CTA's launch-time pool: 768 threads x 80 = 61,440 registers
+        // = 512 x 96 (softmax) + 128 x 40 (epilogue) + 128 x 56 (MMA / TMA / alloc).
+        reg_inc<96>();
         const uint32_t t = warp >> 3;                               // tile 0 / 1
         const uint32_t h = (warp >> 2) & 1;                         // keys [64h, 64h+64) of every block
         const uint32_t r = (warp & 3) * 32 + lane;                  // row within the tile == TMEM lane
@@ -231,13 +233,13 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         pv_waited = true;
                         tc_fence_after();
 #pragma unroll 1
-                        for (int c = 0; c < D / 64; ++c) {          // this half's D/2 columns
-                            uint32_t o[32];
-                            tmem_ld32(tO + c * 32, o);
+                        for (int c = 0; c < D / 32; ++c) {          // this half's D/2 columns, 16 at a time (register budget)
+                            uint32_t o[16];
+                            tmem_ld16(tO + c * 16, o);
                             tmem_wait_ld();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tO + c * 32, o);
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st16(tO + c * 16, o);
                         }
                         tmem_wait_st();
                     }
@@ -253,9 +255,13 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 // pairs take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-                uint32_t pk[2][16];
+                // P_t is still being read by PV_t of the previous block until pv_done (normally long complete:
+                // that MMA was issued a whole softmax block ago).
+                if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
+                    uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
@@ -267,14 +273,10 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             e.y = ex2(x.y);
                         }
                         if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
-                        pk[c][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
+                        pk[i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
                     }
+                    tmem_st16(tP + c * 16, pk);
                 }
-                // P_t is still being read by PV_t of the previous block until pv_done.
-                if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
-                tc_fence_after();
-                tmem_st16(tP, pk[0]);
-                tmem_st16(tP + 16, pk[1]);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar(h ? B_PFULLB + t : B_PFULL + t));
