@@ -255,7 +255,8 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
             snprintf(name, sizeof(name), "%s", kNames[path_ - kVariantBase]);
             if (path_ - kVariantBase == 2) smem_use = aule_kp::FwdCfgV4<128>::SMEM_BYTES;
         }
-        return launch(d, fn, name, grid, 1, 1, v4 ? 512 : (unsigned)FwdCfg<128>::THREADS, smem_use, stream, params);
+        (void)v4;
+        return launch(d, fn, name, grid, 1, 1, 512, smem_use, stream, params);
     }
     SimtParams p;
     memset(&p, 0, sizeof(p));

@@ -31,33 +31,10 @@ struct FwdParams {
                               // 0: 256 rows of one q-head
 };
 
-// v5 layout: Q 2 tiles | K/V ring (4 x [128 keys][D]) | row-max exchange | row statistics | mbarriers.
-// (no O staging: the epilogue stores O from registers).  TMEM: one shared S buffer, P0, P1, O0, O1.
-template <int D>
-struct FwdCfg {
-    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
-    static constexpr int THREADS = 768;                         // 16 softmax + 4 epilogue + MMA + TMA + alloc + 1 warps
-    static constexpr int NS = (D == 128) ? 4 : 8;               // K/V ring stages
-    static constexpr int CHUNKS = D / 64;                       // 128-byte swizzle chunks per row
-    static constexpr uint32_t CHUNK_BYTES = 128 * 128;          // [128 rows][128 B]
-    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
-    static constexpr uint32_t OFF_Q = 0;
-    static constexpr uint32_t OFF_KV = OFF_Q + 2 * TILE_BYTES;
-    static constexpr uint32_t OFF_XMAX = OFF_KV + NS * TILE_BYTES;   // float [parity 2][tile 2][half 2][128]
-    static constexpr uint32_t OFF_STAT = OFF_XMAX + 8 * 128 * 4;     // float l[tile 2][half 2][128], m[tile 2][128]
-    static constexpr uint32_t OFF_BAR = OFF_STAT + 6 * 128 * 4;
-    static constexpr int NBAR = 21 + 2 * NS;
-    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
-    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
-    // TMEM columns (512 allocated)
-    static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 192, COL_O0 = 256, COL_O1 = 256 + D;
-};
-
-// v4 layout (kept for the A/B baseline kernel attn_fwd_sm100_v4.cu)
 // v4 layout: Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
 // tile | row statistics | mbarriers.  TMEM: one shared S buffer, P0, P1, O0, O1.
 template <int D>
-struct FwdCfgV4 {
+struct FwdCfg {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
     static constexpr int NS = (D == 128) ? 4 : 8;               // K/V ring stages
     static constexpr int CHUNKS = D / 64;                       // 128-byte swizzle chunks per row
@@ -75,7 +52,9 @@ struct FwdCfgV4 {
     static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 192, COL_O0 = 256, COL_O1 = 256 + D;
 };
 
-// v3 layout (kept for the A/B baseline kernel attn_fwd_sm100_v3.cu)
+template <int D> using FwdCfgV4 = FwdCfg<D>;     // the A/B baseline kernel (attn_fwd_sm100_v4.cu) shares the layout
+
+// v3 layout (historical)
 template <int D>
 struct FwdCfgV3 {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
