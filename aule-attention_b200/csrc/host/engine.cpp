@@ -115,11 +115,11 @@ std::string Engine::load_device(int ordinal) {
                                               (int)BwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d128)");
     }
     static const char* kVariants[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
-                                       "aule_fwd_sm100_bf16_d128_v4", "aule_fwd_sm100_bf16_d128_e2"};
+                                       "aule_fwd_sm100_bf16_d128_e2", nullptr};
     for (int v = 0; v < 4 && e.empty(); ++v) {
         if (!kVariants[v]) continue;
         e = get(&d.fwd_sm100_var[v], kVariants[v]);
-        const int smem = (v == 2) ? (int)aule_kp::FwdCfgV4<128>::SMEM_BYTES : (int)FwdCfg<128>::SMEM_BYTES;
+        const int smem = (int)FwdCfg<128>::SMEM_BYTES;
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem),
                       "cuFuncSetAttribute(smem variant)");
@@ -230,7 +230,6 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk;
         // GQA/MQA groups with an even number of q-heads: a work item pairs two q-heads of one KV head
         // (equal trip counts, shared K/V tiles); otherwise 256 rows of one head.
-        const bool v4 = path_ == kVariantBase + 2;     // A/B baseline kernel (512 threads, v4 shared-memory layout)
         p.pair_heads = ((s.Hq / s.Hkv) % 2 == 0 && pair_heads_enabled_) ? 1 : 0;
         p.o = (void*)o;
         p.num_q_super = p.pair_heads ? (s.Sq + 127) / 128 : (s.Sq + 255) / 256;
@@ -250,12 +249,10 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         unsigned smem_use = smem;
         if (path_ >= kVariantBase && path_ < kVariantBase + 4 && dtype == kBF16 && d128 && d.fwd_sm100_var[path_ - kVariantBase]) {
             static const char* kNames[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
-                                            "aule_fwd_sm100_bf16_d128_v4", "aule_fwd_sm100_bf16_d128_e2"};
+                                            "aule_fwd_sm100_bf16_d128_e2", ""};
             fn = d.fwd_sm100_var[path_ - kVariantBase];
             snprintf(name, sizeof(name), "%s", kNames[path_ - kVariantBase]);
-            if (path_ - kVariantBase == 2) smem_use = aule_kp::FwdCfgV4<128>::SMEM_BYTES;
         }
-        (void)v4;
         return launch(d, fn, name, grid, 1, 1, 512, smem_use, stream, params);
     }
     SimtParams p;

@@ -12,12 +12,9 @@
 //   warps 0-3   softmax, tile 0   (thread == query row: S TMEM -> registers, exp2, P -> TMEM)
 //   warps 4-7   softmax, tile 1
 //   warps 8-11  epilogue          (O: TMEM -> regs -> 1/l -> SMEM -> TMA store; LSE)
-//   warp  12    Q K^T issuer      (one elected thread issues every S = Q K^T tcgen05.mma)
-//   warp  14    P V issuer        (one elected thread issues every O += P V tcgen05.mma; two issuers because one
-//                                  thread's ~85 instructions per 8-MMA group starved the tensor pipe at 67 %, and a
-//                                  ready Q K^T must not queue behind a P V that is still waiting for its softmax)
+//   warp  12    MMA issuer        (one elected thread issues every tcgen05.mma)
 //   warp  13    TMA producer      (one elected thread issues every bulk tensor load)
-//   warp  15    TMEM allocator
+//   warp  14    TMEM allocator
 //
 // TMEM (512 columns): S [0,128) shared by both tiles | P0 [128,192) | P1 [192,256) |
 //                     O0 [256,256+D) | O1 [256+D,256+2D).
@@ -26,8 +23,8 @@
 // S/P aliasing of v3 and with it the serial chain  softmax(j) -> P V -> Q K^T(j+1) -> softmax(j+1):
 // the next Q K^T of a tile is issued as soon as the OTHER tile's softmax has drained S, and runs
 // under this tile's exp phase, so the softmax warps (the MUFU-bound stage) never wait for it.
-// Issue order: Q K^T thread  QK_0(0) QK_1(0) QK_0(1) | QK_1(j+1) QK_0(j+2) ... (each gated only by s_free);
-//              P V thread    PV_0(j) PV_1(j) ...                                (each gated by p_full of its tile).
+// Steady-state issue order of the MMA thread (all waits blocking, order == readiness order):
+//     PV_0(j)  QK_1(j+1)  PV_1(j)  QK_0(j+2)  PV_0(j+1)  QK_1(j+2)  ...
 // Hazards: P_t is rewritten for block j+1 only after pv_done[t] (commit after PV_t(j)); the rare
 // in-place O_t rescale waits for the same barrier; S is handed over through s_free (128 arrivals
 // after the tcgen05.ld of S completes).
@@ -151,7 +148,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmO);
     }
-    if (warp == 15) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    if (warp == 14) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -349,17 +346,19 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         if (issuer) tma_store_wait_all<0>();
     } else {
         reg_dec<64>();
-        // The K/V ring carries tiles in the order K0 K1 V0 K2 V1 K3 ... (per work item).  The two issuing threads walk
-        // the same sequence; each waits only for the tiles it consumes and steps over the others.
         if (warp == 12) {
-            // ================================================= Q K^T issuer (one elected thread)
+            // ================================================= MMA issuer
             if (elect_one()) {
-                Ring ring;
+                Ring ring;                                          // next K/V ring slot to acquire
+                uint32_t gpv0 = 0, gpv1 = 0;                        // PV_t issued so far (parity of p_full / p_fullb)
                 uint32_t nqk = 0;                                   // Q K^T issued so far (parity of s_free)
                 uint32_t it = 0;
+                // Descriptors are (constant high word, low word = const | addr>>4); stepping along K
+                // is an immediate add on the low word (the 14-bit address field never carries).
                 constexpr uint32_t HI_K_HI = uint32_t(HI_K >> 32), HI_K_LO = uint32_t(HI_K);
+                constexpr uint32_t HI_V_HI = uint32_t(HI_V >> 32), HI_V_LO = uint32_t(HI_V);
                 auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
-                auto acquire = [&]() -> uint32_t {                  // next ring slot holds a K tile: wait for it
+                auto acquire = [&]() -> uint32_t {                  // wait for the next tile of the load order
                     const uint32_t st = ring.stage;
                     mbar_wait<HOT_HINT>(bar(B_KVFULL + st), ring.phase);
                     ring.advance<NS>();
@@ -379,52 +378,6 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     }
                     mma_commit(bar(B_SFULL + t));
                 };
-                for (uint32_t w; next_work(p, it, w); ++it) {
-                    const Work wk = decode(p, w);
-                    const uint32_t n0 = wk.n0, n1 = wk.n1;          // n0 <= n1, n1 >= 1
-                    // S alternates between the tiles: QK_0(0) QK_1(0) QK_0(1) | QK_1(1) QK_0(2) | QK_1(2) QK_0(3) | ...
-                    uint32_t k_cur = acquire();                     // K_0
-                    mbar_wait(bar(B_QFULL + 0), it & 1);
-                    issue_qk(0, k_cur);
-                    if (n0 == 1) mma_commit(bar(B_QEMPTY + 0));
-                    mbar_wait(bar(B_QFULL + 1), it & 1);
-                    issue_qk(1, k_cur);
-                    if (n1 == 1) mma_commit(bar(B_QEMPTY + 1));
-                    mma_commit(bar(B_KVFULL + NS + k_cur));         // K_0 released
-                    uint32_t k_next = 0, k_next2 = 0;               // stages of K_{j+1}, K_{j+2}
-                    if (n1 > 1) {
-                        k_next = acquire();                         // K_1
-                        if (1 < n0) {
-                            issue_qk(0, k_next);
-                            if (n0 == 2) mma_commit(bar(B_QEMPTY + 0));
-                        }
-                    }
-                    for (uint32_t j = 0; j < n1; ++j) {
-                        ring.advance<NS>();                         // V_j belongs to the P V issuer
-                        if (j + 1 < n1) {
-                            issue_qk(1, k_next);                    // QK_1(j+1): last user of K_{j+1}
-                            if (j + 1 == n1 - 1) mma_commit(bar(B_QEMPTY + 1));
-                            mma_commit(bar(B_KVFULL + NS + k_next));
-                        }
-                        if (j + 2 < n1) {
-                            k_next2 = acquire();                    // K_{j+2}
-                            if (j + 2 < n0) {
-                                issue_qk(0, k_next2);
-                                if (j + 2 == n0 - 1) mma_commit(bar(B_QEMPTY + 0));
-                            }
-                        }
-                        k_next = k_next2;
-                    }
-                }
-            }
-        } else if (warp == 14) {
-            // ================================================= P V issuer (one elected thread)
-            if (elect_one()) {
-                Ring ring;
-                uint32_t gpv0 = 0, gpv1 = 0;                        // PV_t issued so far (parity of p_full / p_fullb)
-                uint32_t it = 0;
-                constexpr uint32_t HI_V_HI = uint32_t(HI_V >> 32), HI_V_LO = uint32_t(HI_V);
-                auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
                 auto issue_pv = [&](uint32_t t, uint32_t vstage, bool first, bool last) {   // O_t (+)= P_t V
                     uint32_t& gpv = t ? gpv1 : gpv0;
                     const uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
@@ -447,17 +400,43 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 };
                 for (uint32_t w; next_work(p, it, w); ++it) {
                     const Work wk = decode(p, w);
-                    const uint32_t n0 = wk.n0, n1 = wk.n1;
-                    ring.advance<NS>();                             // K_0
-                    if (n1 > 1) ring.advance<NS>();                 // K_1
+                    const uint32_t n0 = wk.n0, n1 = wk.n1;          // n0 <= n1, n1 >= 1
+                    // ---- prologue: QK_0(0) QK_1(0) QK_0(1)
+                    uint32_t k_cur = acquire();                     // K_0
+                    mbar_wait(bar(B_QFULL + 0), it & 1);
+                    issue_qk(0, k_cur);
+                    if (n0 == 1) mma_commit(bar(B_QEMPTY + 0));
+                    mbar_wait(bar(B_QFULL + 1), it & 1);
+                    issue_qk(1, k_cur);
+                    if (n1 == 1) mma_commit(bar(B_QEMPTY + 1));
+                    mma_commit(bar(B_KVFULL + NS + k_cur));         // K_0 released
+                    uint32_t k_next = 0, k_next2 = 0;               // stages of K_{j+1}, K_{j+2}
+                    if (n1 > 1) {
+                        k_next = acquire();                         // K_1
+                        if (1 < n0) {
+                            issue_qk(0, k_next);
+                            if (n0 == 2) mma_commit(bar(B_QEMPTY + 0));
+                        }
+                    }
+                    // ---- main loop
                     for (uint32_t j = 0; j < n1; ++j) {
-                        const uint32_t v = ring.stage;              // V_j
-                        mbar_wait<HOT_HINT>(bar(B_KVFULL + v), ring.phase);
-                        ring.advance<NS>();
+                        const uint32_t v = acquire();               // V_j
                         if (j < n0) issue_pv(0, v, j == 0, j == n0 - 1);
+                        if (j + 1 < n1) {
+                            issue_qk(1, k_next);                    // QK_1(j+1): last user of K_{j+1}
+                            if (j + 1 == n1 - 1) mma_commit(bar(B_QEMPTY + 1));
+                            mma_commit(bar(B_KVFULL + NS + k_next));
+                        }
                         issue_pv(1, v, j == 0, j == n1 - 1);
                         mma_commit(bar(B_KVFULL + NS + v));         // V_j released
-                        if (j + 2 < n1) ring.advance<NS>();         // K_{j+2}
+                        if (j + 2 < n1) {
+                            k_next2 = acquire();                    // K_{j+2}
+                            if (j + 2 < n0) {
+                                issue_qk(0, k_next2);
+                                if (j + 2 == n0 - 1) mma_commit(bar(B_QEMPTY + 0));
+                            }
+                        }
+                        k_next = k_next2;
                     }
                 }
             }
@@ -499,7 +478,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 15) tmem_dealloc<512>(tmem);
+    if (warp == 14) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace fwd100
@@ -526,7 +505,7 @@ AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, 
 AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
 AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false, AULE_FWD_HINT)
 AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false, AULE_FWD_HINT)
-// tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v))
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0, true, AULE_FWD_HINT)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 2, true, AULE_FWD_HINT)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, true, 0u)
+// tuning variants of the headline kernel (selected with aule_set_kernel_path(16 + v)); see tools/sweep_variants.py
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0, true, AULE_FWD_HINT)      // MUFU only
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 2, true, AULE_FWD_HINT)      // 50 % polynomial exp2
+AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, false, AULE_FWD_HINT)     // F2FP (round-to-nearest) packing

@@ -52,29 +52,6 @@ struct FwdCfg {
     static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 192, COL_O0 = 256, COL_O1 = 256 + D;
 };
 
-template <int D> using FwdCfgV4 = FwdCfg<D>;     // the A/B baseline kernel (attn_fwd_sm100_v4.cu) shares the layout
-
-// v3 layout (historical)
-template <int D>
-struct FwdCfgV3 {
-    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
-    static constexpr int NS = (D == 128) ? 3 : 6;               // K/V ring stages
-    static constexpr int CHUNKS = D / 64;                       // 128-byte swizzle chunks per row
-    static constexpr uint32_t CHUNK_BYTES = 128 * 128;          // [128 rows][128 B]
-    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
-    static constexpr uint32_t OFF_Q = 0;
-    static constexpr uint32_t OFF_KV = OFF_Q + 2 * TILE_BYTES;
-    static constexpr uint32_t OFF_O = OFF_KV + NS * TILE_BYTES;
-    static constexpr uint32_t OFF_STAT = OFF_O + 2 * TILE_BYTES;   // float l[2][128], m[2][128]
-    static constexpr uint32_t OFF_BAR = OFF_STAT + 4 * 128 * 4;
-    static constexpr int NBAR = 18 + 2 * NS;
-    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
-    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
-    // TMEM columns
-    static constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 256 + D;
-};
-
-
 // ---- tcgen05 backward (attn_bwd_sm100.cu) ---------------------------------------------
 struct BwdParams {
     float* dq_ws;             // [B,Hq,Sq,D] fp32, zero-initialised: dQ accumulates here (unscaled)
