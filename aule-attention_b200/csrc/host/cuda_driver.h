@@ -39,6 +39,7 @@ namespace aule {
     X(cuMemcpyHtoDAsync, cuMemcpyHtoDAsync_v2)                                                   \
     X(cuMemcpyDtoHAsync, cuMemcpyDtoHAsync_v2)                                                   \
     X(cuMemsetD8Async, cuMemsetD8Async)                                                          \
+    X(cuMemsetD32Async, cuMemsetD32Async)                                                        \
     X(cuStreamCreate, cuStreamCreate)                                                            \
     X(cuStreamDestroy, cuStreamDestroy_v2)                                                       \
     X(cuStreamSynchronize, cuStreamSynchronize)                                                  \

@@ -125,6 +125,7 @@ std::string Engine::load_device(int ordinal) {
                       "cuFuncSetAttribute(smem variant)");
     }
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
+    if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, 1024 * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_compute, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_out, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
@@ -144,6 +145,7 @@ void Engine::shutdown() {
         drv_.cuCtxSynchronize();
         for (int i = 0; i < 9; ++i)
             if (d.stage[i]) drv_.cuMemFree(d.stage[i]);
+        if (d.sched) drv_.cuMemFree(d.sched);
         if (d.s_in) drv_.cuStreamDestroy(d.s_in);
         if (d.s_compute) drv_.cuStreamDestroy(d.s_compute);
         if (d.s_out) drv_.cuStreamDestroy(d.s_out);
@@ -236,9 +238,19 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         const uint64_t tiles = (uint64_t)p.num_q_super * (p.pair_heads ? s.Hq / 2 : s.Hq) * s.B;
         if (tiles > 0xffffffffull) return "problem too large (work-item count exceeds 2^32)";
         p.num_tiles = (uint32_t)tiles;
+        {   // keep ~32 MiB of K/V (two tensors, 16-bit) live per scheduling run so that it stays in the 126 MB L2
+            const uint64_t unit_bytes = 2ull * s.Sk * s.D * 2ull;
+            const uint64_t upr = std::max<uint64_t>(1, (32ull << 20) / std::max<uint64_t>(unit_bytes, 1));
+            p.units_per_run = (uint32_t)std::min<uint64_t>(upr, (uint64_t)s.B * s.Hkv);
+            if (!l2_runs_enabled_) p.units_per_run = s.B * s.Hkv;
+        }
         p.scale = scale;
         p.scale_log2 = scale * 1.4426950408889634f;
         p.causal = causal ? 1 : 0;
+        // one zeroed work counter per launch, from a ring (a slot is reused 1024 launches later)
+        const CUdeviceptr counter = d.sched + 4ull * (d.sched_next++ & 1023u);
+        if (!(e = check(drv_.cuMemsetD32Async(counter, 0, 1, stream), "cuMemsetD32Async(scheduler counter)")).empty()) return e;
+        p.sched_counter = (uint32_t*)counter;
         const bool d128 = s.D == 128;
         const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
         const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)d.sm_count);

@@ -50,6 +50,9 @@ struct Device {
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    // per-launch work counters of the forward kernel's dynamic scheduler (ring of 1024 x u32, zeroed per launch)
+    CUdeviceptr sched = 0;
+    uint32_t sched_next = 0;
     // grow-only staging buffers for host-pointer calls: q k v o lse do dq dk dv
     CUdeviceptr stage[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     size_t stage_cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -94,8 +97,9 @@ public:
     std::string copy_d2h(int dev, void* dst, CUdeviceptr src, size_t bytes);
     std::string synchronize(int dev);
 
-    // path: 0 auto, 1 force CUDA-core kernels, 16+v tuning variant v; bit 8 (256) disables head pairing.
-    void set_kernel_path(int32_t p) { pair_heads_enabled_ = !(p & 256); path_ = p & 255; }
+    // path: 0 auto, 1 force CUDA-core kernels, 16+v tuning variant v; bit 8 (256) disables head pairing,
+    // bit 9 (512) disables the L2-residency runs of the work-item order.
+    void set_kernel_path(int32_t p) { pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); path_ = p & 255; }
     uint64_t launch_count() const { return launches_; }
     const char* last_kernel() const { return last_kernel_.c_str(); }
 
@@ -112,6 +116,7 @@ private:
     bool ready_ = false;
     int32_t path_ = kAuto;
     bool pair_heads_enabled_ = true;
+    bool l2_runs_enabled_ = true;
     uint64_t launches_ = 0;
     std::string last_kernel_ = "none";
 };

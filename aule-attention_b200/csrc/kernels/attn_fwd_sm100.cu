@@ -56,7 +56,9 @@ enum : int {
     B_STFULL = 16,   // softmax t -> epilogue: row statistics written
     B_STEMPTY = 18,  // epilogue -> softmax t: row statistics consumed
     B_SFREE = 20,    // softmax (either tile) -> MMA: S copied to registers
-    B_KVFULL = 21    // + NS: kv_empty
+    B_WKFULL = 21,   // scheduler -> all roles: work_ring[slot] holds the next work item (4 slots)
+    B_WKEMPTY = 25,  // all roles -> scheduler: slot consumed (1 MMA + 256 softmax + 128 epilogue arrivals)
+    B_KVFULL = 29    // + NS: kv_empty
 };
 
 struct Work {
@@ -64,31 +66,36 @@ struct Work {
     uint32_t dbh, drow;          // tile t covers q-head (bh + t*dbh), rows [row0 + t*drow, +128)
 };
 
-// Work items, heaviest first under causal masking.
-//  pair_heads: 128 query rows x the two q-heads (2h, 2h+1) of one KV group -> both tiles walk the same
-//              K/V blocks and have EQUAL trip counts (no idle slot for tile 0), K/V tiles shared.
-//  otherwise : 256 query rows of one q-head (tile 1 needs one more block than tile 0 under causal).
+// Work items.  A "unit" is one (batch, kv-head) with the Hq/Hkv query heads that share it.  Units are scheduled in
+// runs of `units_per_run` (chosen by the host so that a run's K/V stays L2-resident: without it every unit is in
+// flight at once and K/V is re-fetched from HBM for every query block -- measured 1.65 GB of DRAM reads per
+// config-C launch against 0.40 GB compulsory).  Inside a run items go heaviest-first (causal), so the snake
+// deal below balances every run on its own.
+//  pair_heads: item = 128 query rows x the two q-heads (2h, 2h+1) of the unit -> both tiles walk the same K/V
+//              blocks and have EQUAL trip counts (no idle slot for tile 0).
+//  otherwise : item = 256 query rows of one q-head (tile 1 needs one more block than tile 0 under causal).
 __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     Work t;
     const uint32_t nkb = (p.Sk + 127) / 128;
+    const uint32_t G = p.Hq / p.Hkv, NU = p.B * p.Hkv;
+    const uint32_t ipu = p.pair_heads ? G / 2 : G;                   // items per (query level, unit)
+    const uint32_t ipr = p.num_q_super * p.units_per_run * ipu;      // items per full run
+    const uint32_t run = w / ipr, lw = w - run * ipr;
+    const uint32_t uir = min(p.units_per_run, NU - run * p.units_per_run);   // units in this run (last may be short)
+    const uint32_t per = uir * ipu;
+    const uint32_t qrev = lw / per, rem = lw - qrev * per;
+    const uint32_t unit = run * p.units_per_run + rem / ipu, hh = rem % ipu;
+    const uint32_t b = unit / p.Hkv, hk = unit - b * p.Hkv;
+    const uint32_t ql = p.causal ? (p.num_q_super - 1 - qrev) : qrev; // heaviest first under causal
+    t.bkv = unit;
     if (p.pair_heads) {
-        const uint32_t hp_n = p.Hq / 2, per = hp_n * p.B;
-        const uint32_t qrev = w / per, rem = w - qrev * per;
-        const uint32_t hp = rem % hp_n, b = rem / hp_n;
-        const uint32_t qb = p.causal ? (p.num_q_super - 1 - qrev) : qrev;
-        t.bh = b * p.Hq + 2 * hp;
-        t.bkv = b * p.Hkv + (2 * hp) / (p.Hq / p.Hkv);
-        t.row0 = qb * 128;
-        t.n0 = t.n1 = p.causal ? min(nkb, qb + 1) : nkb;
+        t.bh = b * p.Hq + hk * G + 2 * hh;
+        t.row0 = ql * 128;
+        t.n0 = t.n1 = p.causal ? min(nkb, ql + 1) : nkb;
         t.dbh = 1; t.drow = 0;
     } else {
-        const uint32_t per = p.Hq * p.B;
-        const uint32_t qrev = w / per;
-        t.bh = w - qrev * per;
-        const uint32_t qs = p.causal ? (p.num_q_super - 1 - qrev) : qrev;
-        const uint32_t hq = t.bh % p.Hq, b = t.bh / p.Hq;
-        t.bkv = b * p.Hkv + hq / (p.Hq / p.Hkv);
-        t.row0 = qs * 256;
+        t.bh = b * p.Hq + hk * G + hh;
+        t.row0 = ql * 256;
         t.n0 = p.causal ? min(nkb, t.row0 / 128 + 1) : nkb;    // KV blocks tile 0 needs (diagonal included)
         t.n1 = p.causal ? min(nkb, t.row0 / 128 + 2) : nkb;    // n0 <= n1 always
         t.dbh = 0; t.drow = 128;
@@ -96,14 +103,16 @@ __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     return t;
 }
 
-// Static persistent schedule: work items are sorted heaviest-first (decode) and dealt to the CTAs in
-// boustrophedon ("snake") order, round r going left-to-right when even and right-to-left when odd, which
-// balances the monotonically decreasing causal weights to ~0.3% (plain round-robin: 3.4% on config C).
-__device__ __forceinline__ bool next_work(const FwdParams& p, uint32_t it, uint32_t& w) {
-    const uint32_t base = it * gridDim.x;
-    if (base >= p.num_tiles) return false;
-    w = base + ((it & 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x);
-    return w < p.num_tiles;          // only the last round can be partial
+// Dynamic persistent schedule: the TMA-producer thread claims work items with an atomic counter (items are sorted
+// run by run, heaviest first inside a run, see decode) and publishes them through a 4-slot ring in shared memory;
+// every other role consumes the ring in order.  A claimed index >= num_tiles is the stop sentinel.
+__device__ __forceinline__ bool get_work(const FwdParams& p, uint32_t bar_full0, uint32_t bar_empty0,
+                                         const volatile uint32_t* ring, uint32_t it, uint32_t& w) {
+    const uint32_t slot = it & 3;
+    mbar_wait(bar_full0 + 8 * slot, (it >> 2) & 1);
+    w = ring[slot];
+    mbar_arrive(bar_empty0 + 8 * slot);
+    return w < p.num_tiles;
 }
 
 struct Ring {
@@ -124,6 +133,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     auto bar = [&](int i) -> uint32_t { return sb + C::OFF_BAR + 8u * i; };
     float* sStat = reinterpret_cast<float*>(smem + C::OFF_STAT);          // [l0 | l1 | m0 | m1] x 128
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
+    volatile uint32_t* work_ring = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_WORK);
 
     if (threadIdx.x == 0 && (sb & 1023u)) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
 
@@ -141,6 +151,10 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             mbar_init(bar(B_STEMPTY + t), 128); // epilogue threads
         }
         mbar_init(bar(B_SFREE), 128);           // softmax threads of whichever tile owns S
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar(B_WKFULL + i), 1);     // scheduler (TMA thread)
+            mbar_init(bar(B_WKEMPTY + i), 385);  // 1 MMA + 256 softmax + 128 epilogue threads
+        }
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_KVFULL + s), 1);
             mbar_init(bar(B_KVFULL + NS + s), 1);
@@ -169,7 +183,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         const uint32_t tP = tmem + lane_addr + (t ? C::COL_P1 : C::COL_P0);
         const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
         uint32_t g = 0, it = 0;                                     // g: blocks processed so far by this tile
-        for (uint32_t w; next_work(p, it, w); ++it) {
+        for (uint32_t w; get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w); ++it) {
             const Work wk = decode(p, w);
             const uint32_t n = t ? wk.n1 : wk.n0;
             const uint32_t trow0 = wk.row0 + t * wk.drow;
@@ -295,7 +309,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         const bool issuer = (warp == 8 && lane == 0);
         const uint32_t sO = sb + C::OFF_O;
         uint32_t it = 0;
-        for (uint32_t w; next_work(p, it, w); ++it) {
+        for (uint32_t w; get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w); ++it) {
             const Work wk = decode(p, w);
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
@@ -398,7 +412,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     mma_commit(bar(B_PVDONE + t));
                     if (last) mma_commit(bar(B_OFULL + t));
                 };
-                for (uint32_t w; next_work(p, it, w); ++it) {
+                for (uint32_t w; get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w); ++it) {
                     const Work wk = decode(p, w);
                     const uint32_t n0 = wk.n0, n1 = wk.n1;          // n0 <= n1, n1 >= 1
                     // ---- prologue: QK_0(0) QK_1(0) QK_0(1)
@@ -455,7 +469,16 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         tma_load_3d(dst + c * C::CHUNK_BYTES, map, full, c * 64, (int32_t)(j * 128), (int32_t)bkv);
                     ring.advance<NS>();
                 };
-                for (uint32_t w; next_work(p, it, w); ++it) {
+                for (;; ++it) {
+                    uint32_t w;
+                    {   // claim and publish the next work item
+                        const uint32_t slot = it & 3;
+                        mbar_wait(bar(B_WKEMPTY + slot), ((it >> 2) & 1) ^ 1);
+                        w = atomicAdd(p.sched_counter, 1u);
+                        work_ring[slot] = w;
+                        mbar_arrive(bar(B_WKFULL + slot));
+                        if (w >= p.num_tiles) break;
+                    }
                     const Work wk = decode(p, w);
                     load_kv(tmK, 0, wk.bkv);
                     for (uint32_t t = 0; t < 2; ++t) {

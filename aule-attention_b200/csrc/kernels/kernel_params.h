@@ -29,6 +29,8 @@ struct FwdParams {
     int32_t causal;
     int32_t pair_heads;       // 1: a work item is 128 rows x 2 adjacent q-heads of one KV group (equal trip counts);
                               // 0: 256 rows of one q-head
+    uint32_t units_per_run;   // (batch, kv-head) units whose work items are scheduled together (L2 residency of K/V)
+    uint32_t* sched_counter;  // zero-initialised per launch: next unclaimed work item (dynamic persistent scheduler)
 };
 
 // v4 layout: Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
@@ -44,8 +46,9 @@ struct FwdCfg {
     static constexpr uint32_t OFF_KV = OFF_Q + 2 * TILE_BYTES;
     static constexpr uint32_t OFF_O = OFF_KV + NS * TILE_BYTES;
     static constexpr uint32_t OFF_STAT = OFF_O + 1 * TILE_BYTES;   // float l[2][128], m[2][128]
-    static constexpr uint32_t OFF_BAR = OFF_STAT + 4 * 128 * 4;
-    static constexpr int NBAR = 21 + 2 * NS;
+    static constexpr uint32_t OFF_WORK = OFF_STAT + 4 * 128 * 4;   // uint32 work_ring[4]
+    static constexpr uint32_t OFF_BAR = OFF_WORK + 16;
+    static constexpr int NBAR = 29 + 2 * NS;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
     // TMEM columns (512 allocated)
