@@ -67,14 +67,17 @@ struct BwdParams {
 template <int D>
 struct BwdCfg {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
+    static constexpr int THREADS = 288;                         // 8 compute warps (2 column halves x 128 rows) + 1 issuer warp
     static constexpr int CHUNKS = D / 64;
     static constexpr uint32_t CHUNK_BYTES = 128 * 128;          // [128 rows][128 B]
     static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
-    static constexpr uint32_t OFF_K = 0, OFF_V = TILE_BYTES, OFF_Q = 2 * TILE_BYTES, OFF_DO = 3 * TILE_BYTES;
-    static constexpr uint32_t OFF_P = 4 * TILE_BYTES;           // P  [128 q rows][128 keys] 16-bit
+    static constexpr uint32_t OFF_K = 0, OFF_V = TILE_BYTES;
+    static constexpr uint32_t OFF_Q = 2 * TILE_BYTES;           // Q double-buffered
+    static constexpr uint32_t OFF_DO = 4 * TILE_BYTES;
+    static constexpr uint32_t OFF_P = 5 * TILE_BYTES;           // P  [128 q rows][128 keys] 16-bit
     static constexpr uint32_t OFF_DS = OFF_P + 2 * CHUNK_BYTES; // dS same shape
     static constexpr uint32_t OFF_BAR = OFF_DS + 2 * CHUNK_BYTES;
-    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 64;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 96;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
 };
 
