@@ -72,9 +72,12 @@ def run(name, B, Hq, Hkv, S, D, dtype=torch.bfloat16, bwd=False, yard=True):
 
 
 if __name__ == "__main__":
-    run("B bf16 MHA [4,32,2048,64]", 4, 32, 32, 2048, 64)
-    run("C bf16 GQA [8,32,4096,128]", 8, 32, 8, 4096, 128)
-    run("D/8 bf16 [1,4,32768,128] (one GPU's head shard of config D)", 1, 4, 4, 32768, 128, yard=False)
-    run("E bf16 fwd+bwd [2,16,1024,64]", 2, 16, 16, 1024, 64, bwd=True)
+    only_bwd = len(sys.argv) > 1 and sys.argv[1] == "bwd"
+    if not only_bwd:
+        run("B bf16 MHA [4,32,2048,64]", 4, 32, 32, 2048, 64)
+        run("C bf16 GQA [8,32,4096,128]", 8, 32, 8, 4096, 128)
+        run("D/8 bf16 [1,4,32768,128] (one GPU's head shard of config D)", 1, 4, 4, 32768, 128, yard=False)
+    run("E bf16 fwd+bwd [2,16,1024,64]", 2, 16, 16, 1024, 64, bwd=True, yard=not only_bwd)
     run("C/2 bwd bf16 GQA [4,32,4096,128]", 4, 32, 8, 4096, 128, bwd=True, yard=False)
-    run("C fp16 GQA [8,32,4096,128]", 8, 32, 8, 4096, 128, dtype=torch.float16, yard=False)
+    if not only_bwd:
+        run("C fp16 GQA [8,32,4096,128]", 8, 32, 8, 4096, 128, dtype=torch.float16, yard=False)
