@@ -255,3 +255,49 @@ def test_tensor_core_backward_agrees_with_cuda_core_backward(aule):
             lib.aule_set_kernel_path(0)
     for a, b in zip(*grads):
         assert (a - b).abs().max().item() / b.abs().max().item() <= 1e-2
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,D,causal", [
+    (1, 6, 2, 300, 300, 128, True),     # GQA group of 3 (odd): 256-row work items, not head-paired
+    (3, 4, 4, 520, 520, 64, True),      # MHA, 3 batches
+    (5, 8, 1, 260, 260, 128, True),     # MQA group of 8, five (batch, kv-head) units
+    (2, 10, 5, 130, 900, 64, False),    # cross attention, group 2, ragged both ways
+])
+def test_scheduler_shapes(aule, B, Hq, Hkv, Sq, Sk, D, causal):
+    """Work-item decode paths of the dynamic scheduler: odd / even GQA groups, several units per run."""
+    q, k, v = ref_inputs(B, Hq, Sq, D, Hkv=Hkv, Sk=Sk)
+    out, lse, (rq, rk, rv), kern = _run(aule, q, k, v, causal, "bf16")
+    assert "sm100" in kern
+    exp, exp_lse = orc.attention_ref(rq, rk, rv, causal=causal)
+    assert orc.rel_err_to_scale(out, exp) <= BF16_TOL
+    np.testing.assert_allclose(lse, exp_lse, rtol=2e-3, atol=2e-3)
+
+
+def test_long_sequence_short_runs(aule):
+    """BASELINE.json configs[3] shape per GPU at 8-way head sharding: [1,4,32768,128] causal. K/V of one head is
+    16 MiB, so the L2-residency runs hold 2 units; oracle on sampled row blocks + row 0 == v[0]."""
+    import torch
+    from aule import cuda_flash
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q, k, v = (torch.randn(1, 4, 32768, 128, device="cuda", dtype=torch.bfloat16, generator=g) for _ in range(3))
+    out, lse = cuda_flash.forward_with_lse(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[:, :, 0, :], v[:, :, 0, :])
+    fq, fk, fv = (t.float().cpu().numpy() for t in (q, k, v))
+    for (h, r0) in ((0, 0), (1, 12345), (3, 32640), (2, 20000)):
+        exp, el = orc.attention_rows(fq, fk, fv, 0, h, r0, 128, causal=True)
+        assert orc.rel_err_to_scale(out[0, h, r0:r0 + 128].float().cpu().numpy(), exp) <= BF16_TOL
+        np.testing.assert_allclose(lse[0, h, r0:r0 + 128].cpu().numpy(), el, rtol=2e-3, atol=2e-3)
+
+
+def test_many_small_calls_reuse_scheduler_counters(aule):
+    """More launches than the 1024-entry ring of per-launch work counters."""
+    import torch
+    from aule import cuda_flash
+    q, k, v = (torch.randn(1, 2, 128, 64, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    ref, _ = cuda_flash.forward_with_lse(q, k, v, causal=True)
+    for _ in range(1100):
+        out, _ = cuda_flash.forward_with_lse(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
