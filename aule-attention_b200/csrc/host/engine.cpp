@@ -219,7 +219,8 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
     if (!(scale > 0.f)) scale = 1.0f / sqrtf((float)s.D);   // triton_flash.py:394-395
     if (window == 0) window = -1;
 
-    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && window < 0 &&
+    // tensor-core path: 16-bit, D in {64,128}, full attention or a causal sliding window
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && (window < 0 || causal) &&
                     path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0;
     if (tc) {
         CUtensorMap tmQ, tmK, tmV, tmO;
@@ -247,6 +248,7 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         p.scale = scale;
         p.scale_log2 = scale * 1.4426950408889634f;
         p.causal = causal ? 1 : 0;
+        p.window = causal ? window : -1;
         // one zeroed work counter per launch, from a ring (a slot is reused 1024 launches later)
         const CUdeviceptr counter = d.sched + 4ull * (d.sched_next++ & 1023u);
         if (!(e = check(drv_.cuMemsetD32Async(counter, 0, 1, stream), "cuMemsetD32Async(scheduler counter)")).empty()) return e;

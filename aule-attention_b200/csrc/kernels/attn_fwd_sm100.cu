@@ -63,6 +63,7 @@ enum : int {
 
 struct Work {
     uint32_t bh, bkv, row0, n0, n1;
+    uint32_t j0;                 // first K/V block (left edge of a sliding window; 0 otherwise)
     uint32_t dbh, drow;          // tile t covers q-head (bh + t*dbh), rows [row0 + t*drow, +128)
 };
 
@@ -88,6 +89,7 @@ __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     const uint32_t b = unit / p.Hkv, hk = unit - b * p.Hkv;
     const uint32_t ql = p.causal ? (p.num_q_super - 1 - qrev) : qrev; // heaviest first under causal
     t.bkv = unit;
+    t.j0 = 0;
     if (p.pair_heads) {
         t.bh = b * p.Hq + hk * G + 2 * hh;
         t.row0 = ql * 128;
@@ -99,6 +101,10 @@ __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
         t.n0 = p.causal ? min(nkb, t.row0 / 128 + 1) : nkb;    // KV blocks tile 0 needs (diagonal included)
         t.n1 = p.causal ? min(nkb, t.row0 / 128 + 2) : nkb;    // n0 <= n1 always
         t.dbh = 0; t.drow = 128;
+    }
+    if (p.window > 0 && t.row0 + 1 > (uint32_t)p.window) {           // blocks entirely left of the window are skipped
+        t.j0 = min((t.row0 + 1 - (uint32_t)p.window) / 128, t.n0 - 1);  // common start (tile 0's first row is the leftmost)
+        t.n0 -= t.j0; t.n1 -= t.j0;
     }
     return t;
 }
@@ -198,21 +204,24 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(bar(B_SFREE));                          // S may be overwritten by the next Q K^T
-                const bool need_mask = (p.causal && j * 128 + 127 > trow0) || ((j + 1) * 128 > p.Sk);
-                if (need_mask) {                                    // diagonal / ragged-tail blocks only: kept rolled (I-cache)
+                const uint32_t jg = wk.j0 + j;                      // global K/V block index
+                const bool win_edge = p.window > 0 && jg * 128 + (uint32_t)p.window < trow0 + 128;   // some key left of a row's window
+                const bool need_mask = (p.causal && jg * 128 + 127 > trow0) || ((jg + 1) * 128 > p.Sk) || win_edge;
+                if (need_mask) {                                    // diagonal / ragged-tail / window-edge blocks only: kept rolled (I-cache)
                     const uint32_t lim = p.causal ? min(grow, p.Sk - 1) : p.Sk - 1;   // last visible key
-                    const int32_t thr = (int32_t)lim - (int32_t)(j * 128);            // columns > thr are masked (a suffix)
+                    const int32_t thr = (int32_t)lim - (int32_t)(jg * 128);           // local columns > thr are masked (a suffix)
+                    const int32_t lo = p.window > 0 ? (int32_t)grow - p.window + 1 - (int32_t)(jg * 128) : -1;   // local columns < lo are masked (a prefix)
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
-                        if (thr >= c * 32 + 31) continue;
+                        if (thr >= c * 32 + 31 && lo <= c * 32) continue;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const uint32_t neg = (c * 32 + i > thr) ? 0xff800000u : 0u;   // -inf
+                            const bool dead = (c * 32 + i > thr) || (c * 32 + i < lo);
                             // dynamic c: select the chunk without dynamic register indexing
-                            if (c == 0) s[0][i] = neg ? neg : s[0][i];
-                            else if (c == 1) s[1][i] = neg ? neg : s[1][i];
-                            else if (c == 2) s[2][i] = neg ? neg : s[2][i];
-                            else s[3][i] = neg ? neg : s[3][i];
+                            if (c == 0) s[0][i] = dead ? 0xff800000u : s[0][i];
+                            else if (c == 1) s[1][i] = dead ? 0xff800000u : s[1][i];
+                            else if (c == 2) s[2][i] = dead ? 0xff800000u : s[2][i];
+                            else s[3][i] = dead ? 0xff800000u : s[3][i];
                         }
                     }
                 }
@@ -480,7 +489,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         if (w >= p.num_tiles) break;
                     }
                     const Work wk = decode(p, w);
-                    load_kv(tmK, 0, wk.bkv);
+                    load_kv(tmK, wk.j0, wk.bkv);
                     for (uint32_t t = 0; t < 2; ++t) {
                         mbar_wait(bar(B_QEMPTY + t), (it & 1) ^ 1);
                         const uint32_t full = bar(B_QFULL + t);
@@ -490,10 +499,10 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             tma_load_3d(sb + C::OFF_Q + t * C::TILE_BYTES + c * C::CHUNK_BYTES, tmQ, full, c * 64,
                                         (int32_t)(wk.row0 + t * wk.drow), (int32_t)(wk.bh + t * wk.dbh));
                     }
-                    if (wk.n1 > 1) load_kv(tmK, 1, wk.bkv);         // same order as the MMA thread acquires
+                    if (wk.n1 > 1) load_kv(tmK, wk.j0 + 1, wk.bkv);   // same order as the MMA thread acquires
                     for (uint32_t j = 0; j < wk.n1; ++j) {
-                        load_kv(tmV, j, wk.bkv);
-                        if (j + 2 < wk.n1) load_kv(tmK, j + 2, wk.bkv);
+                        load_kv(tmV, wk.j0 + j, wk.bkv);
+                        if (j + 2 < wk.n1) load_kv(tmK, wk.j0 + j + 2, wk.bkv);
                     }
                 }
             }

@@ -27,6 +27,7 @@ struct FwdParams {
     float scale;              // softmax scale (natural)
     float scale_log2;         // scale * log2(e)
     int32_t causal;
+    int32_t window;           // > 0 with causal: key j visible to query i iff 0 <= i - j < window; <= 0: none
     int32_t pair_heads;       // 1: a work item is 128 rows x 2 adjacent q-heads of one KV group (equal trip counts);
                               // 0: 256 rows of one q-head
     uint32_t units_per_run;   // (batch, kv-head) units whose work items are scheduled together (L2 residency of K/V)

@@ -301,3 +301,23 @@ def test_many_small_calls_reuse_scheduler_counters(aule):
         out, _ = cuda_flash.forward_with_lse(q, k, v, causal=True)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("window", [1, 64, 128, 200, 1000, 5000])
+@pytest.mark.parametrize("shape", [(1, 4, 2, 1024, 128), (2, 3, 3, 700, 64)])
+def test_sliding_window_tensor_core(aule, window, shape):
+    """causal sliding window (keep 0 <= i - j < W, attention_f32.comp:176-178) on the tcgen05
+    kernel: blocks left of the window are skipped, edge blocks are masked on both sides."""
+    import torch
+    from aule import ffi
+    B, Hq, Hkv, S, D = shape
+    q, k, v = ref_inputs(B, Hq, S, D, Hkv=Hkv)
+    tq, tk, tv = (torch.from_numpy(x).cuda().to(torch.bfloat16) for x in (q, k, v))
+    out = aule.flash_attention(tq, tk, tv, causal=True, window_size=window)
+    torch.cuda.synchronize()
+    assert ffi.load_library().aule_last_kernel().decode() == f"aule_fwd_sm100_bf16_d{D}"
+    rq, rk, rv = (t.float().cpu().numpy() for t in (tq, tk, tv))
+    exp, _ = orc.attention_ref(rq, rk, rv, causal=True, window=window)
+    got = out.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert orc.rel_err_to_scale(got, exp) <= BF16_TOL, orc.rel_err_to_scale(got, exp)
