@@ -274,6 +274,15 @@ int32_t aule_attention_forward_host(const void* q, const void* k, const void* v,
     return 0;
 }
 
+int32_t aule_rope_dptr(uint64_t x, uint64_t out, uint64_t cos, uint64_t sin, uint32_t B, uint32_t H, uint32_t S,
+                       uint32_t D, int32_t dtype, int32_t inverse, int32_t device, uint64_t cu_stream) {
+    if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
+    std::string e = g_engine.rope(device, (CUstream)cu_stream, x, out, cos, sin, (uint64_t)B * H, S, D, dtype,
+                                  inverse ? -1.f : 1.f);
+    if (!e.empty()) { set_error("RoPE failed: %s", e.c_str()); return -4; }
+    return 0;
+}
+
 int32_t aule_device_count(void) { return g_engine.ready() ? g_engine.device_count() : -1; }
 int32_t aule_get_sm_count(int32_t device) {
     aule::Device* d = g_engine.ready() ? g_engine.by_ordinal(device) : nullptr;

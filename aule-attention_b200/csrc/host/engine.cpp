@@ -124,6 +124,7 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem),
                       "cuFuncSetAttribute(smem variant)");
     }
+    for (int t = 0; t < 3 && e.empty(); ++t) e = get(&d.rope[t], std::string("aule_rope_") + kDtypeSuffix[t]);
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
     if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, 1024 * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
@@ -508,6 +509,24 @@ std::string Engine::smoke_multiply(int dev, const float* in, float* out, uint32_
     if (!(e = launch(d, d.smoke, "aule_smoke_multiply", (n + 255) / 256, 1, 1, 256, 0, d.s_compute, params)).empty()) return e;
     if (!(e = check(drv_.cuMemcpyDtoHAsync(out, b, (size_t)n * 4, d.s_compute), "download")).empty()) return e;
     return check(drv_.cuStreamSynchronize(d.s_compute), "smoke kernel");
+}
+
+std::string Engine::rope(int dev, CUstream stream, CUdeviceptr x, CUdeviceptr out, CUdeviceptr cos, CUdeviceptr sin,
+                         uint64_t bh, uint32_t S, uint32_t D, int32_t dtype, float sign) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    if (dtype < 0 || dtype > 2) return "unsupported dtype (0=f32, 1=bf16, 2=f16)";
+    if (!x || !out || !cos || !sin) return "null device pointer";
+    if (D == 0 || (D & 1) || !S || !bh) return "RoPE needs an even head_dim and non-empty tensors";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    uint64_t rows = bh * S;
+    void* params[] = {&x, &out, &cos, &sin, &rows, &S, &D, &sign};
+    char name[32];
+    snprintf(name, sizeof(name), "aule_rope_%s", kDtypeSuffix[dtype]);
+    const uint64_t work = rows * (D / 2);
+    return launch(d, d.rope[dtype], name, (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)d.sm_count * 16), 1, 1, 256, 0, stream, params);
 }
 
 std::string Engine::mem_alloc(int dev, size_t bytes, CUdeviceptr* out) {

@@ -47,6 +47,7 @@ struct Device {
     CUfunction bwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_cvt[3] = {nullptr, nullptr, nullptr};
+    CUfunction rope[3] = {nullptr, nullptr, nullptr};
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;
@@ -89,6 +90,9 @@ public:
                               const float* lse, void* dq, void* dk, void* dv, const AttnShape& s, int32_t dtype,
                               float scale, bool causal, int* stage_code);
     std::string smoke_multiply(int dev, const float* in, float* out, uint32_t n);
+    // out = RoPE(x) (half-split convention), x/out: [rows_total = B*H*S, D] of `dtype`, cos/sin: [S, D/2] fp32.
+    std::string rope(int dev, CUstream stream, CUdeviceptr x, CUdeviceptr out, CUdeviceptr cos, CUdeviceptr sin,
+                     uint64_t bh, uint32_t S, uint32_t D, int32_t dtype, float sign);
 
     // Raw memory for the handle-table tensors (device 0).
     std::string mem_alloc(int dev, size_t bytes, CUdeviceptr* out);

@@ -320,3 +320,29 @@ extern "C" __global__ void aule_cvt_bf16_to_f32(const __nv_bfloat16* in, float* 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = __bfloat162float(in[i]);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Rotary position embedding, half-split convention of the reference's Triton path
+// (python/aule/triton_flash.py:680-703 apply_rope_separate; rotate_half(x) = [-x2, x1]):
+//   out[d]       = x[d]       * cos[s,d] - x[d + D/2] * sin[s,d]
+//   out[d + D/2] = x[d + D/2] * cos[s,d] + x[d]       * sin[s,d]          d < D/2,  cos/sin: [S, D/2] fp32
+// `sign` = -1 applies the transpose (inverse rotation), which is what the backward pass needs.
+// Memory-bound elementwise pass (x read once, out written once); fp32 math.
+template <typename T>
+__device__ __forceinline__ void rope_body(const T* x, T* out, const float* cs, const float* sn, uint64_t rows,
+                                          uint32_t S, uint32_t D, float sign) {
+    const uint32_t half = D / 2;
+    const uint64_t total = rows * half;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = i / half;
+        const uint32_t d = (uint32_t)(i - row * half);
+        const uint32_t s = (uint32_t)(row % S);
+        const float c = cs[(size_t)s * half + d], sv = sign * sn[(size_t)s * half + d];
+        const float x1 = Elem<T>::ld(x, row * D + d), x2 = Elem<T>::ld(x, row * D + d + half);
+        Elem<T>::st(out, row * D + d, x1 * c - x2 * sv);
+        Elem<T>::st(out, row * D + d + half, x2 * c + x1 * sv);
+    }
+}
+extern "C" __global__ void aule_rope_f32(const float* x, float* out, const float* cs, const float* sn, uint64_t rows, uint32_t S, uint32_t D, float sign) { rope_body(x, out, cs, sn, rows, S, D, sign); }
+extern "C" __global__ void aule_rope_bf16(const __nv_bfloat16* x, __nv_bfloat16* out, const float* cs, const float* sn, uint64_t rows, uint32_t S, uint32_t D, float sign) { rope_body(x, out, cs, sn, rows, S, D, sign); }
+extern "C" __global__ void aule_rope_f16(const __half* x, __half* out, const float* cs, const float* sn, uint64_t rows, uint32_t S, uint32_t D, float sign) { rope_body(x, out, cs, sn, rows, S, D, sign); }

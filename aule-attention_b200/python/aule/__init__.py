@@ -128,6 +128,27 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
 attention = flash_attention      # alias, __init__.py:275
 
 
+def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1):
+    """RoPE (half-split convention) on Q and K, then attention -- reference: triton_flash.py:561-603."""
+    from .cuda_flash import flash_attention_rope as _impl
+    _validate(q, k, v)
+    if not _cuda_available:
+        raise RuntimeError("aule (B200 build): CUDA sm_100 backend not available and there is no CPU fallback: "
+                           + _backend_errors.get('cuda', 'unknown error'))
+    return _impl(q, k, v, cos, sin, causal=causal, scale=scale, window_size=window_size)
+
+
+def precompute_rope_frequencies(seq_len, head_dim, base=10000.0, device="cuda", dtype=None):
+    from .cuda_flash import precompute_rope_frequencies as _impl
+    import torch
+    return _impl(seq_len, head_dim, base=base, device=device, dtype=dtype or torch.float32)
+
+
+def apply_rope_separate(q, k, cos, sin):
+    from .cuda_flash import apply_rope_separate as _impl
+    return _impl(q, k, cos, sin)
+
+
 # =============================================================================
 # PyTorch SDPA compatibility layer (reference __init__.py:288-442)
 # =============================================================================
@@ -220,6 +241,7 @@ def print_backend_info():
 
 __all__ = [
     "flash_attention", "attention", "scaled_dot_product_attention",
+    "flash_attention_rope", "precompute_rope_frequencies", "apply_rope_separate",
     "install", "uninstall",
     "get_available_backends", "get_backend_errors", "get_backend_info", "print_backend_info",
     "Aule", "GpuTensor", "AuleError",

@@ -110,3 +110,82 @@ def flash_attention_host(q, k, v, causal=True, scale=None, window_size=-1, lse=N
                                          1 if causal else 0, int(window_size), int(device))
     _check(rc, "Attention failed")
     return out
+
+
+# =============================================================================
+# RoPE (mirror of triton_flash.py:561-703: flash_attention_rope, precompute_rope_frequencies, apply_rope_separate)
+# =============================================================================
+class _RopeFunc(torch.autograd.Function):
+    """x -> RoPE(x) with the half-split convention (triton_flash.py:680-703). The backward pass is the
+    transposed rotation (same kernel, -sin)."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin):
+        lib = ffi.ensure_init()
+        B, H, S, D = x.shape
+        cdt = x.dtype if x.dtype in _TORCH_TO_AULE else torch.float32
+        xc = x.to(cdt).contiguous()
+        cos = cos.reshape(-1, D // 2)[:S].to(device=x.device, dtype=torch.float32).contiguous()
+        sin = sin.reshape(-1, D // 2)[:S].to(device=x.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(xc)
+        dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        rc = lib.aule_rope_dptr(xc.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, H, S, D,
+                                _TORCH_TO_AULE[cdt], 0, dev, torch.cuda.current_stream(dev).cuda_stream)
+        _check(rc, "RoPE failed")
+        ctx.save_for_backward(cos, sin)
+        ctx.dev, ctx.cdt, ctx.orig = dev, cdt, x.dtype
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        cos, sin = ctx.saved_tensors
+        lib = ffi.ensure_init()
+        B, H, S, D = g.shape
+        gc = g.to(ctx.cdt).contiguous()
+        out = torch.empty_like(gc)
+        rc = lib.aule_rope_dptr(gc.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, H, S, D,
+                                _TORCH_TO_AULE[ctx.cdt], 1, ctx.dev, torch.cuda.current_stream(ctx.dev).cuda_stream)
+        _check(rc, "RoPE backward failed")
+        return out.to(ctx.orig), None, None
+
+
+def apply_rope(x, cos, sin):
+    """RoPE on the GPU through the C ABI (differentiable)."""
+    return _RopeFunc.apply(x, cos, sin)
+
+
+def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1):
+    """Mirror of triton_flash.py:561-603: RoPE on Q and K (half-split convention), then the fused attention.
+    The rotation is a separate memory-bound pass over Q and K here (2 x (|Q|+|K|) bytes), not fused into the
+    tcgen05 kernel, which reads its operands with TMA straight into the MMA layout."""
+    assert q.dim() == 4 and k.dim() == 4 and v.dim() == 4
+    assert q.shape[-1] == k.shape[-1] == v.shape[-1]
+    assert k.shape[1] == v.shape[1] and k.shape[2] == v.shape[2]
+    assert q.shape[1] % k.shape[1] == 0
+    assert cos is not None and sin is not None, "cos and sin are required for RoPE"
+    return flash_attention_cuda(apply_rope(q, cos, sin), apply_rope(k, cos, sin), v, causal=causal, scale=scale,
+                                window_size=window_size)
+
+
+def precompute_rope_frequencies(seq_len, head_dim, base=10000.0, device="cuda", dtype=torch.float32):
+    """triton_flash.py:640-677: cos, sin of shape [seq_len, head_dim // 2]."""
+    half_dim = head_dim // 2
+    freqs = 1.0 / (base ** (torch.arange(0, half_dim, device=device, dtype=dtype) / half_dim))
+    positions = torch.arange(seq_len, device=device, dtype=dtype)
+    angles = positions[:, None] * freqs[None, :]
+    return torch.cos(angles), torch.sin(angles)
+
+
+def apply_rope_separate(q, k, cos, sin):
+    """triton_flash.py:680-703: the plain torch formulation (reference for tests)."""
+    def rotate_half(x):
+        x1 = x[..., :x.shape[-1] // 2]
+        x2 = x[..., x.shape[-1] // 2:]
+        return torch.cat([-x2, x1], dim=-1)
+
+    seq_len = q.shape[2]
+    cos = cos[:seq_len].unsqueeze(0).unsqueeze(0)
+    sin = sin[:seq_len].unsqueeze(0).unsqueeze(0)
+    cos_full = torch.cat([cos, cos], dim=-1)
+    sin_full = torch.cat([sin, sin], dim=-1)
+    return q * cos_full + rotate_half(q) * sin_full, k * cos_full + rotate_half(k) * sin_full

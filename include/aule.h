@@ -163,6 +163,15 @@ AULE_API int32_t aule_attention_forward_host(const void* q, const void* k, const
                                              int32_t dtype, float scale, int32_t causal,
                                              int32_t window, int32_t device);
 
+/* Rotary position embedding on raw device pointers, the half-split convention of the reference's
+ * Triton path (python/aule/triton_flash.py:680-703 apply_rope_separate):
+ *   out[d] = x[d] cos[s,d] - x[d+D/2] sin[s,d],  out[d+D/2] = x[d+D/2] cos[s,d] + x[d] sin[s,d]
+ * x/out: [B,H,S,D] of `dtype`, cos/sin: [S, D/2] fp32; inverse != 0 applies the transpose (backward pass).
+ * The step immediately before the hot path (flash_attention_rope, triton_flash.py:561-603). */
+AULE_API int32_t aule_rope_dptr(uint64_t x, uint64_t out, uint64_t cos, uint64_t sin, uint32_t B, uint32_t H,
+                                uint32_t S, uint32_t D, int32_t dtype, int32_t inverse, int32_t device,
+                                uint64_t cu_stream);
+
 /* Device bookkeeping. */
 AULE_API int32_t aule_device_count(void);               /* sm_100 devices usable, -1 not init */
 AULE_API int32_t aule_get_sm_count(int32_t device);     /* 148 on B200 */

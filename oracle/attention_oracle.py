@@ -168,6 +168,17 @@ def attention_bwd_ref(q, k, v, do, causal=True, scale=None, acc=np.float64):
     return dq, dk, dv, o, lse
 
 
+def rope_ref(x, cos, sin):
+    """Half-split RoPE, restating apply_rope_separate (python/aule/triton_flash.py:680-703):
+    x_rot = x * [cos,cos] + rotate_half(x) * [sin,sin], rotate_half(x) = [-x2, x1]. x: [B,H,S,D], cos/sin: [S,D/2]."""
+    x = np.asarray(x, np.float64)
+    S, D = x.shape[2], x.shape[3]
+    c = np.concatenate([cos[:S], cos[:S]], axis=-1)[None, None].astype(np.float64)
+    s = np.concatenate([sin[:S], sin[:S]], axis=-1)[None, None].astype(np.float64)
+    x1, x2 = x[..., :D // 2], x[..., D // 2:]
+    return x * c + np.concatenate([-x2, x1], axis=-1) * s
+
+
 # --------------------------------------------------------------------------
 # 3. Comparison helpers in the reference's tolerance SHAPE.
 #    tests/test_attention.zig:60-77 : max_abs < atol OR max_rel < rtol,

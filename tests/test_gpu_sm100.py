@@ -321,3 +321,36 @@ def test_sliding_window_tensor_core(aule, window, shape):
     got = out.float().cpu().numpy()
     assert np.isfinite(got).all()
     assert orc.rel_err_to_scale(got, exp) <= BF16_TOL, orc.rel_err_to_scale(got, exp)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_rope_entry_points(aule, dtype):
+    """flash_attention_rope / precompute_rope_frequencies / apply_rope_separate
+    (python/aule/triton_flash.py:561-703, half-split convention) vs the oracle, forward and backward."""
+    import torch
+    td = {"bf16": torch.bfloat16, "f32": torch.float32}[dtype]
+    B, Hq, Hkv, S, D = 2, 8, 2, 256, 64
+    cos, sin = aule.precompute_rope_frequencies(S, D)
+    assert cos.shape == (S, D // 2) and sin.shape == (S, D // 2)
+    torch.manual_seed(0)
+    q = torch.randn(B, Hq, S, D, device="cuda").to(td).requires_grad_()
+    k = torch.randn(B, Hkv, S, D, device="cuda").to(td).requires_grad_()
+    v = torch.randn(B, Hkv, S, D, device="cuda").to(td).requires_grad_()
+    out = aule.flash_attention_rope(q, k, v, cos, sin, causal=True)
+    do = torch.randn_like(out)
+    out.backward(do)
+    # oracle: rotate in fp64, then attention; gradients flow back through the transposed rotation
+    cn, sn = cos.cpu().numpy(), sin.cpu().numpy()
+    rq, rk, rv, rdo = (t.detach().float().cpu().numpy() for t in (q, k, v, do))
+    qr, kr = orc.rope_ref(rq, cn, sn), orc.rope_ref(rk, cn, sn)
+    exp, _ = orc.attention_ref(qr, kr, rv, causal=True)
+    tol = 2e-2 if dtype == "bf16" else 1e-3      # bf16: q,k are rounded once more after the rotation
+    assert orc.rel_err_to_scale(out.detach().float().cpu().numpy(), exp) <= tol
+    dqr, dkr, dv, _, _ = orc.attention_bwd_ref(qr, kr, rv, rdo, causal=True)
+    dq, dk = orc.rope_ref(dqr, cn, -sn), orc.rope_ref(dkr, cn, -sn)       # transpose of the rotation
+    for g, e in ((q.grad, dq), (k.grad, dk), (v.grad, dv)):
+        assert orc.rel_err_to_scale(g.float().cpu().numpy(), e) <= tol
+    # the torch formulation of the reference agrees with the kernel
+    q2, k2 = aule.apply_rope_separate(q.detach().float(), k.detach().float(), cos, sin)
+    from aule import cuda_flash
+    assert (cuda_flash.apply_rope(q.detach(), cos, sin).float() - q2).abs().max().item() <= (2e-2 if dtype == "bf16" else 1e-5)

@@ -210,3 +210,20 @@ def test_bf16_helpers():
     ref = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
     assert np.array_equal(orc.bf16_round(x), ref)
     assert np.array_equal(orc.from_bf16_bits(orc.to_bf16_bits(x)), ref)
+
+
+def test_rope_ref_matches_reference_formulation():
+    """oracle rope_ref vs the reference's apply_rope_separate formula (triton_flash.py:680-703) in torch."""
+    torch = pytest.importorskip("torch")
+    S, D = 12, 8
+    half = D // 2
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, half, dtype=torch.float64) / half))
+    ang = torch.arange(S, dtype=torch.float64)[:, None] * freqs[None, :]
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    x = torch.randn(2, 3, S, D, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    x1, x2 = x[..., :half], x[..., half:]
+    exp = x * torch.cat([cos, cos], -1)[None, None] + torch.cat([-x2, x1], -1) * torch.cat([sin, sin], -1)[None, None]
+    np.testing.assert_allclose(orc.rope_ref(x.numpy(), cos.numpy(), sin.numpy()), exp.numpy(), rtol=1e-12, atol=1e-14)
+    # rotation is orthogonal: transpose (negated sin) inverts it
+    back = orc.rope_ref(exp.numpy(), cos.numpy(), -sin.numpy())
+    np.testing.assert_allclose(back, x.numpy(), rtol=1e-12, atol=1e-13)
