@@ -114,16 +114,15 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)BwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d128)");
     }
-    static const char* kVariants[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
-                                       "aule_fwd_sm100_bf16_d128_e2", nullptr};
-    for (int v = 0; v < 4 && e.empty(); ++v) {
-        if (!kVariants[v]) continue;
-        e = get(&d.fwd_sm100_var[v], kVariants[v]);
-        const int smem = (int)FwdCfg<128>::SMEM_BYTES;
-        if (e.empty())
-            e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem),
-                      "cuFuncSetAttribute(smem variant)");
-    }
+    for (int dd = 0; dd < 2 && e.empty(); ++dd)
+        for (int v = 0; v < 3 && e.empty(); ++v) {
+            const std::string nm = std::string("aule_fwd_sm100_bf16_d") + (dd ? "128" : "64") + "_e" + char('0' + v);
+            e = get(&d.fwd_sm100_var[dd][v], nm);
+            if (e.empty())
+                e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[dd][v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                                  dd ? (int)FwdCfg<128>::SMEM_BYTES : (int)FwdCfg<64>::SMEM_BYTES),
+                          "cuFuncSetAttribute(smem variant)");
+        }
     for (int t = 0; t < 3 && e.empty(); ++t) e = get(&d.rope[t], std::string("aule_rope_") + kDtypeSuffix[t]);
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
     if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, 1024 * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
@@ -262,11 +261,9 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
         CUfunction fn = d.fwd_sm100[dtype][d128 ? 1 : 0];
         unsigned smem_use = smem;
-        if (path_ >= kVariantBase && path_ < kVariantBase + 4 && dtype == kBF16 && d128 && d.fwd_sm100_var[path_ - kVariantBase]) {
-            static const char* kNames[4] = {"aule_fwd_sm100_bf16_d128_e0", "aule_fwd_sm100_bf16_d128_e1",
-                                            "aule_fwd_sm100_bf16_d128_e2", ""};
-            fn = d.fwd_sm100_var[path_ - kVariantBase];
-            snprintf(name, sizeof(name), "%s", kNames[path_ - kVariantBase]);
+        if (path_ >= kVariantBase && path_ < kVariantBase + 3 && dtype == kBF16 && d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase]) {
+            fn = d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase];
+            snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d%u_e%d", s.D, path_ - kVariantBase);
         }
         return launch(d, fn, name, grid, 1, 1, 512, smem_use, stream, params);
     }

@@ -43,7 +43,7 @@ struct Device {
     CUfunction bwd_dq_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dkv_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
-    CUfunction fwd_sm100_var[4] = {nullptr, nullptr, nullptr, nullptr};   // bf16 d128 tuning variants (_e0.._e3)
+    CUfunction fwd_sm100_var[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // bf16 tuning variants [D==128][v]
     CUfunction bwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_cvt[3] = {nullptr, nullptr, nullptr};

@@ -541,3 +541,6 @@ AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false, AULE_FWD_HI
 AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 0, true, AULE_FWD_HINT)      // MUFU only
 AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 2, true, AULE_FWD_HINT)      // 50 % polynomial exp2
 AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 1, false, AULE_FWD_HINT)     // F2FP (round-to-nearest) packing
+AULE_FWD100(aule_fwd_sm100_bf16_d64_e0, 64, true, 0, true, AULE_FWD_HINT)
+AULE_FWD100(aule_fwd_sm100_bf16_d64_e1, 64, true, 2, true, AULE_FWD_HINT)
+AULE_FWD100(aule_fwd_sm100_bf16_d64_e2, 64, true, 3, true, AULE_FWD_HINT)
