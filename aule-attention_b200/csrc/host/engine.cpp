@@ -106,13 +106,20 @@ std::string Engine::load_device(int ordinal) {
         e = get(&d.bwd_sm100[t][0], std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + "_d64");
         if (e.empty()) e = get(&d.bwd_sm100[t][1], std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + "_d128");
         if (e.empty()) e = get(&d.bwd_delta[t], std::string("aule_bwd_delta_") + kDtypeSuffix[t]);
-        if (e.empty()) e = get(&d.bwd_cvt[t], std::string("aule_bwd_dq_convert_") + kDtypeSuffix[t]);
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)BwdCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d64)");
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)BwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d128)");
+        if (e.empty()) e = get(&d.bwd_dq_sm100[t][0], std::string("aule_bwd_dq_sm100_") + kDtypeSuffix[t] + "_d64");
+        if (e.empty()) e = get(&d.bwd_dq_sm100[t][1], std::string("aule_bwd_dq_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_dq_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::BwdDqCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d64)");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_dq_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::BwdDqCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d128)");
     }
     for (int dd = 0; dd < 2 && e.empty(); ++dd)
         for (int v = 0; v < 3 && e.empty(); ++v) {
@@ -301,13 +308,11 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && path_ != kForceCudaCore &&
                     ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0;
     if (tc) {
-        // Tensor-core backward: Delta pre-pass, fused dK/dV/dQ kernel (dQ reduced in an fp32 workspace), convert.
-        CUdeviceptr ws = 0;
-        const uint64_t nq = (uint64_t)s.B * s.Hq * s.Sq * s.D;
-        e = check(drv_.cuMemAllocAsync(&ws, nq * sizeof(float), stream), "cuMemAllocAsync(dq workspace)");
-        if (e.empty()) e = check(drv_.cuMemsetD8Async(ws, 0, nq * sizeof(float), stream), "cuMemsetD8Async(dq workspace)");
+        // Tensor-core backward: Delta pre-pass, then the dK/dV kernel (key block outer) and the dQ kernel (query block
+        // outer).  No atomics and no workspace beyond Delta: bit-reproducible.
+        const bool d128 = s.D == 128;
         char name[64];
-        if (e.empty()) {
+        {
             uint64_t rows = (uint64_t)s.B * s.Hq * s.Sq;
             uint32_t D = s.D;
             void* params[] = {&o, &d_o, &delta, &rows, &D};
@@ -323,26 +328,26 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             if (e.empty()) e = make_tmap(&tmdK, dtype, dk, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
             if (e.empty()) e = make_tmap(&tmdV, dtype, dv, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
             BwdParams bp;
-            bp.dq_ws = (float*)ws; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
+            bp.dq_out = (void*)dq; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
             bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
-            if (e.empty() && ctas > 0x7fffffffull) e = "problem too large (backward grid exceeds 2^31 CTAs)";
+            const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
+            if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
             if (e.empty()) {
-                const bool d128 = s.D == 128;
                 void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
                 snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
                 e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, (unsigned)BwdCfg<128>::THREADS,
                            d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
             }
+            if (e.empty()) {
+                void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &bp};
+                snprintf(name, sizeof(name), "aule_bwd_dq_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+                e = launch(d, d.bwd_dq_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas_dq, 1, 1,
+                           (unsigned)aule_kp::BwdDqCfg<128>::THREADS,
+                           d128 ? aule_kp::BwdDqCfg<128>::SMEM_BYTES : aule_kp::BwdDqCfg<64>::SMEM_BYTES, stream, params);
+            }
         }
-        if (e.empty()) {
-            uint64_t n = nq;
-            void* params[] = {&ws, &dq, &n, &scale};
-            snprintf(name, sizeof(name), "aule_bwd_dq_convert_%s", kDtypeSuffix[dtype]);
-            e = launch(d, d.bwd_cvt[dtype], name, (unsigned)std::min<uint64_t>((nq / 2 + 255) / 256, 148 * 16), 1, 1, 256, 0, stream, params);
-        }
-        if (ws) drv_.cuMemFreeAsync(ws, stream);
         drv_.cuMemFreeAsync(delta, stream);
         return e;
     }

@@ -58,7 +58,7 @@ struct FwdCfg {
 
 // ---- tcgen05 backward (attn_bwd_sm100.cu) ---------------------------------------------
 struct BwdParams {
-    float* dq_ws;             // [B,Hq,Sq,D] fp32, zero-initialised: dQ accumulates here (unscaled)
+    void* dq_out;             // dQ kernel: [B,Hq,Sq,D] output in the input dtype
     const float* lse;         // [B,Hq,Sq] natural-log LSE of the forward
     const float* delta;       // [B,Hq,Sq] rowsum(O o dO)
     uint32_t B, Hq, Hkv, Sq, Sk;
@@ -77,6 +77,23 @@ struct BwdCfg {
     static constexpr uint32_t OFF_DO = 4 * TILE_BYTES;
     static constexpr uint32_t OFF_P = 5 * TILE_BYTES;           // P  [128 q rows][128 keys] 16-bit
     static constexpr uint32_t OFF_DS = OFF_P + 2 * CHUNK_BYTES; // dS same shape
+    static constexpr uint32_t OFF_BAR = OFF_DS + 2 * CHUNK_BYTES;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 96;           // 10 mbarriers
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+};
+
+// dQ kernel (query block outer): Q, dO resident | K,V double-buffered | dS | barriers
+template <int D>
+struct BwdDqCfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
+    static constexpr int THREADS = 288;
+    static constexpr int CHUNKS = D / 64;
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_Q = 0, OFF_DO = TILE_BYTES;
+    static constexpr uint32_t OFF_K = 2 * TILE_BYTES;           // 2 stages
+    static constexpr uint32_t OFF_V = 4 * TILE_BYTES;           // 2 stages
+    static constexpr uint32_t OFF_DS = 6 * TILE_BYTES;          // dS [128 q rows][128 keys] 16-bit
     static constexpr uint32_t OFF_BAR = OFF_DS + 2 * CHUNK_BYTES;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 96;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
