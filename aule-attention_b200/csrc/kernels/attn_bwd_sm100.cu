@@ -13,9 +13,9 @@
 //     stream through a 2-stage ring, dQ accumulates in TMEM.  S, P and dS are recomputed there (two extra GEMMs and
 //     one extra exp pass) -- measured faster than reducing dQ partials through 4.4 GB of fp32 red.global.add per
 //     config-C/2 launch (experiments/attn_bwd_sm100_v2_fused_atomics.cu.txt), and deterministic.
-// Both are 288-thread CTAs:
-//   warps 0-3 / 4-7  compute: thread == (query row, key half of 64 columns)
-//   warp  8          issuer: one elected thread issues every TMA load and every tcgen05.mma
+// Both are 544-thread CTAs (four compute warps per scheduler hide the TMEM-load / MUFU / barrier latencies):
+//   warps 0-15       compute: thread == (query row, key quarter of 32 columns)
+//   warp  16         issuer: one elected thread issues every TMA load and every tcgen05.mma
 // and both split a step into two phases so that the tensor pipe always has work the compute warps are not waiting on:
 //   P  phase  compute: S (TMEM) -> P = exp2(S*c - LSE*log2e) kept in registers (fp32) [+ 16-bit P -> SMEM]
 //             tensor : dP(i) = dO V^T          (+ dK(i-1) | dQ(j-1), S(j+1) into the second S buffer)
@@ -78,8 +78,8 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     const uint32_t bar_do = bar_kv + 24;            // dO landed
     const uint32_t bar_s = bar_kv + 32;             // S(i) complete (commit)
     const uint32_t bar_dp = bar_kv + 40;            // dP(i) complete (commit)
-    const uint32_t bar_p = bar_kv + 48;             // compute -> issuer: P(i) in SMEM, S columns consumed (256 arrivals)
-    const uint32_t bar_ds = bar_kv + 56;            // compute -> issuer: dS(i) in SMEM, dP columns consumed (256 arrivals)
+    const uint32_t bar_p = bar_kv + 48;             // compute -> issuer: P(i) in SMEM, S columns consumed (512 arrivals)
+    const uint32_t bar_ds = bar_kv + 56;            // compute -> issuer: dS(i) in SMEM, dP columns consumed (512 arrivals)
     const uint32_t bar_dv = bar_kv + 64;            // dV(i) complete (commit): P buffer and dO buffer free
     const uint32_t bar_dk = bar_kv + 72;            // dK(i) complete (commit): dS buffer and Q buffer i&1 free
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
@@ -89,12 +89,12 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     if (threadIdx.x == 0) {
         if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
         mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1); mbar_init(bar_do, 1);
-        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 256); mbar_init(bar_ds, 256);
+        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 512); mbar_init(bar_ds, 512);
         mbar_init(bar_dv, 1); mbar_init(bar_dk, 1);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
-    if (warp == 8) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    if (warp == 16) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -113,7 +113,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     const uint32_t steps_per_head = (i_begin < nqb) ? (nqb - i_begin) : 0;
     const uint32_t nsteps = steps_per_head * group;
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ===================================================== issuer
         if (elect_one()) {
             constexpr uint64_t HI_K = smem_desc_hi(16, 1024);                // K-major SW128
@@ -216,7 +216,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
         }
     } else {
         // ===================================================== compute warps
-        const uint32_t h = warp >> 2;                                // key half: columns [64h, 64h+64)
+        const uint32_t qt = warp >> 2;                               // key quarter: columns [32qt, 32qt+32)
         const uint32_t r = (warp & 3) * 32 + lane;                   // row of the tile == TMEM lane
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
         // row statistics of the NEXT step are fetched one step ahead and only touched one step later
@@ -240,20 +240,18 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
             const bool masked = diag || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
 
             // ---- P phase: P = exp2(S*scale_log2 - LSE*log2e) (fp32, kept in registers) -> 16-bit -> swizzled SMEM
-            float pv[64];
+            float pv[32];
             mbar_wait(bar_s, step & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
                 uint32_t s[32];
-                tmem_ld32(tmem + lane_addr + COL_S + 64 * h + c * 32, s);
+                tmem_ld32(tmem + lane_addr + COL_S + 32 * qt, s);
                 tmem_wait_ld();
-                if (masked) p_from_s<true>(s, pv + 32 * c, p.scale_log2, lse2, key0 + 64 * h + c * 32, row, p.Sk, row_ok, diag);
-                else p_from_s<false>(s, pv + 32 * c, p.scale_log2, lse2, 0, 0, 0, true, false);
+                if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
+                else p_from_s<false>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
             }
             if (step > 0) mbar_wait(bar_dv, (step - 1) & 1);         // dV(step-1) has read the P buffer
-#pragma unroll
-            for (int c = 0; c < 2; ++c) store_row32<BF16>(sP + h * C::CHUNK_BYTES, r, c, pv + 32 * c);
+            store_row32<BF16>(sP + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();                                // generic-proxy writes -> visible to the MMA (async proxy)
             tc_fence_before();
             mbar_arrive(bar_p);
@@ -261,17 +259,15 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
             // ---- dS phase: dS = P o (dP - Delta) -> 16-bit -> swizzled SMEM
             mbar_wait(bar_dp, step & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
                 uint32_t dp[32];
-                tmem_ld32(tmem + lane_addr + COL_DP + 64 * h + c * 32, dp);
+                tmem_ld32(tmem + lane_addr + COL_DP + 32 * qt, dp);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) pv[32 * c + e] *= (__uint_as_float(dp[e]) - delta);
+                for (int e = 0; e < 32; ++e) pv[e] *= (__uint_as_float(dp[e]) - delta);
             }
             if (step > 0) mbar_wait(bar_dk, (step - 1) & 1);         // dK(step-1) has read the dS buffer
-#pragma unroll
-            for (int c = 0; c < 2; ++c) store_row32<BF16>(sdS + h * C::CHUNK_BYTES, r, c, pv + 32 * c);
+            store_row32<BF16>(sdS + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(bar_ds);
@@ -281,11 +277,11 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     // ---- epilogue: dV, dK (x scale) -> 16-bit -> swizzled SMEM (P / dS buffers) -> TMA store
     __syncthreads();                                                 // every MMA is complete (the issuer waited on the last commit)
     tc_fence_after();
-    if (warp < 8) {
-        const uint32_t h = warp >> 2, r = (warp & 3) * 32 + lane;
+    if (warp < 16) {
+        const uint32_t h = (warp >> 2) & 1, r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
-#pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
+        {
+            const int which = warp >> 3;                             // warps 0-7: dV, warps 8-15: dK
             const uint32_t col = (which ? COL_DK : COL_DV) + (D / 2) * h;
             const uint32_t sbuf = which ? sdS : sP;
             const float mul = which ? p.scale : 1.f;
@@ -327,7 +323,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem);
+    if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
 // =====================================================================================================
@@ -345,7 +341,7 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
     const uint32_t bar_kve0 = bar_qdo + 24;         // dQ(j) complete (commit): K/V stage j&1 and the dS buffer free (+8 for odd j)
     const uint32_t bar_s0 = bar_qdo + 40;           // S buffer 0 / 1 complete (commit) (+8)
     const uint32_t bar_dp = bar_qdo + 56;           // dP complete (commit)
-    const uint32_t bar_ds = bar_qdo + 64;           // compute -> issuer: dS in SMEM, S and dP consumed (256 arrivals)
+    const uint32_t bar_ds = bar_qdo + 64;           // compute -> issuer: dS in SMEM, S and dP consumed (512 arrivals)
     const uint32_t bar_done = bar_qdo + 72;         // every MMA complete (commit)
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
     const uint32_t sQ = sb + C::OFF_Q, sdO = sb + C::OFF_DO, sK0 = sb + C::OFF_K, sV0 = sb + C::OFF_V, sdS = sb + C::OFF_DS;
@@ -353,11 +349,11 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
     if (threadIdx.x == 0) {
         if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
         mbar_init(bar_qdo, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1); mbar_init(bar_kve0, 1); mbar_init(bar_kve0 + 8, 1);
-        mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 256); mbar_init(bar_done, 1);
+        mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 512); mbar_init(bar_done, 1);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
-    if (warp == 8) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    if (warp == 16) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -374,7 +370,7 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
     const uint32_t bkv = b * p.Hkv + hq / (p.Hq / p.Hkv);
     const uint32_t n = p.causal ? min(nkb, i + 1) : nkb;             // key blocks 0..n-1 (top-left causal)
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ===================================================== issuer
         if (elect_one()) {
             constexpr uint64_t HI_K = smem_desc_hi(16, 1024);
@@ -454,7 +450,8 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
         }
     } else {
         // ===================================================== compute warps
-        const uint32_t h = warp >> 2;                                // key half: columns [64h, 64h+64)
+        const uint32_t qt = warp >> 2;                               // key quarter: columns [32qt, 32qt+32)
+        const uint32_t h = (warp >> 2) & 1;                          // epilogue (warps 0-7): D half
         const uint32_t r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
         const uint32_t row = i * 128 + r;
@@ -467,31 +464,28 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
             const bool diag = p.causal && (i * 128 < key0 + 128);
             const bool masked = diag || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
             // ---- P phase
-            float pv[64];
+            float pv[32];
             mbar_wait(bar_s0 + 8 * (j & 1), (j >> 1) & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
                 uint32_t s[32];
-                tmem_ld32(tmem + lane_addr + 384 * (j & 1) + 64 * h + c * 32, s);
+                tmem_ld32(tmem + lane_addr + 384 * (j & 1) + 32 * qt, s);
                 tmem_wait_ld();
-                if (masked) p_from_s<true>(s, pv + 32 * c, p.scale_log2, lse2, key0 + 64 * h + c * 32, row, p.Sk, row_ok, diag);
-                else p_from_s<false>(s, pv + 32 * c, p.scale_log2, lse2, 0, 0, 0, true, false);
+                if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
+                else p_from_s<false>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
             }
             // ---- dS phase
             mbar_wait(bar_dp, j & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
                 uint32_t dp[32];
-                tmem_ld32(tmem + lane_addr + COL_DP + 64 * h + c * 32, dp);
+                tmem_ld32(tmem + lane_addr + COL_DP + 32 * qt, dp);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) pv[32 * c + e] *= (__uint_as_float(dp[e]) - delta);
+                for (int e = 0; e < 32; ++e) pv[e] *= (__uint_as_float(dp[e]) - delta);
             }
             if (j > 0) mbar_wait(bar_kve0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);   // dQ(j-1) has read the dS buffer
-#pragma unroll
-            for (int c = 0; c < 2; ++c) store_row32<BF16>(sdS + h * C::CHUNK_BYTES, r, c, pv + 32 * c);
+            store_row32<BF16>(sdS + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(bar_ds);
@@ -499,6 +493,7 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
         // ---- epilogue: dQ (x scale) -> 16-bit -> global (this half's D/2 columns of the row: 64 or 128 contiguous bytes)
         mbar_wait(bar_done, 0);
         tc_fence_after();
+        if (warp < 8) {
         uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.dq_out) + ((stat_off + (row_ok ? row : 0)) * D + (D / 2) * h) * 2);
 #pragma unroll 1
         for (int c = 0; c < D / 64; ++c) {
@@ -517,16 +512,17 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
                 }
             }
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem);
+    if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace bwd100
 
 #define AULE_BWD100(NAME, DD, BF)                                                                        \
-    extern "C" __global__ void __launch_bounds__(288, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
+    extern "C" __global__ void __launch_bounds__(544, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
                                                               const __grid_constant__ CUtensorMap tmK,    \
                                                               const __grid_constant__ CUtensorMap tmV,    \
                                                               const __grid_constant__ CUtensorMap tmdO,   \
@@ -536,7 +532,7 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
         bwd100::bwd_dkv_body<DD, BF>(&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, p);                           \
     }
 #define AULE_BWD100_DQ(NAME, DD, BF)                                                                     \
-    extern "C" __global__ void __launch_bounds__(288, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
+    extern "C" __global__ void __launch_bounds__(544, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
                                                               const __grid_constant__ CUtensorMap tmK,    \
                                                               const __grid_constant__ CUtensorMap tmV,    \
                                                               const __grid_constant__ CUtensorMap tmdO,   \

@@ -68,7 +68,7 @@ struct BwdParams {
 template <int D>
 struct BwdCfg {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
-    static constexpr int THREADS = 288;                         // 8 compute warps (2 column halves x 128 rows) + 1 issuer warp
+    static constexpr int THREADS = 544;                         // 16 compute warps (4 column quarters x 128 rows) + 1 issuer warp
     static constexpr int CHUNKS = D / 64;
     static constexpr uint32_t CHUNK_BYTES = 128 * 128;          // [128 rows][128 B]
     static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
@@ -86,7 +86,7 @@ struct BwdCfg {
 template <int D>
 struct BwdDqCfg {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
-    static constexpr int THREADS = 288;
+    static constexpr int THREADS = 544;
     static constexpr int CHUNKS = D / 64;
     static constexpr uint32_t CHUNK_BYTES = 128 * 128;
     static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
