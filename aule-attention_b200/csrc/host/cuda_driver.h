@@ -34,6 +34,8 @@ namespace aule {
     X(cuMemFree, cuMemFree_v2)                                                                   \
     X(cuMemAllocAsync, cuMemAllocAsync)                                                          \
     X(cuMemFreeAsync, cuMemFreeAsync)                                                            \
+    X(cuDeviceGetDefaultMemPool, cuDeviceGetDefaultMemPool)                                      \
+    X(cuMemPoolSetAttribute, cuMemPoolSetAttribute)                                              \
     X(cuMemcpyHtoD, cuMemcpyHtoD_v2)                                                             \
     X(cuMemcpyDtoH, cuMemcpyDtoH_v2)                                                             \
     X(cuMemcpyHtoDAsync, cuMemcpyHtoDAsync_v2)                                                   \

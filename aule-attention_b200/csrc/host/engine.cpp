@@ -133,6 +133,16 @@ std::string Engine::load_device(int ordinal) {
     for (int t = 0; t < 3 && e.empty(); ++t) e = get(&d.rope[t], std::string("aule_rope_") + kDtypeSuffix[t]);
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
     if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, 1024 * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
+    if (e.empty()) {
+        // The backward's Delta workspace comes from the stream-ordered pool (cuMemAllocAsync). With the default
+        // release threshold (0) the pool hands its memory back to the OS at every synchronisation and the next
+        // call pays a fresh physical allocation (~0.5-1 ms, measured on config E); keep it cached instead.
+        CUmemoryPool pool = nullptr;
+        if (drv_.cuDeviceGetDefaultMemPool(&pool, d.dev) == CUDA_SUCCESS && pool) {
+            cuuint64_t keep = ~0ull;
+            drv_.cuMemPoolSetAttribute(pool, CU_MEMPOOL_ATTR_RELEASE_THRESHOLD, &keep);
+        }
+    }
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_compute, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_out, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
@@ -331,6 +341,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             bp.dq_out = (void*)dq; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
             bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
+            bp.order = bwd_order_;
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";

@@ -102,8 +102,11 @@ public:
     std::string synchronize(int dev);
 
     // path: 0 auto, 1 force CUDA-core kernels, 16+v tuning variant v; bit 8 (256) disables head pairing,
-    // bit 9 (512) disables the L2-residency runs of the work-item order.
-    void set_kernel_path(int32_t p) { pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); path_ = p & 255; }
+    // bit 9 (512) disables the L2-residency runs of the work-item order; bits 10-11 select the backward kernels'
+    // MMA issue order (BwdParams::order, A/B tuning).
+    void set_kernel_path(int32_t p) {
+        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); bwd_order_ = (p >> 10) & 3; path_ = p & 255;
+    }
     uint64_t launch_count() const { return launches_; }
     const char* last_kernel() const { return last_kernel_.c_str(); }
 
@@ -121,6 +124,7 @@ private:
     int32_t path_ = kAuto;
     bool pair_heads_enabled_ = true;
     bool l2_runs_enabled_ = true;
+    int32_t bwd_order_ = 0;
     uint64_t launches_ = 0;
     std::string last_kernel_ = "none";
 };

@@ -64,6 +64,7 @@ struct BwdParams {
     uint32_t B, Hq, Hkv, Sq, Sk;
     float scale, scale_log2;
     int32_t causal;
+    int32_t order;            // MMA issue order (tuning): bit 0: dP(i) before dK(i-1) / dQ(j-1); bit 1: S(i+1) before dV(i)
 };
 template <int D>
 struct BwdCfg {

@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (read with `ncu -i`) into a small markdown file for profiles/.
-usage: python tools/ncu_summary.py gpurun_out/fwd_r1.ncu-rep profiles/r1_fwd_v1.md "note"
+usage: python tools/ncu_summary.py gpurun_out/fwd_r1.ncu-rep profiles/r1_fwd_v1.md "note" [kernel-name-regex]
 """
 import collections
 import csv
@@ -22,14 +22,17 @@ KEYS = [
 ]
 
 
+FILTER = []
+
+
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, *FILTER, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
 
 def stalls(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, *FILTER, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -54,6 +57,8 @@ def stalls(rep):
 def main():
     rep, dst = sys.argv[1], sys.argv[2]
     note = sys.argv[3] if len(sys.argv) > 3 else ""
+    if len(sys.argv) > 4:
+        FILTER.extend(["-k", "regex:" + sys.argv[4]])
     hdr, units, rows = raw(rep)
     with open(dst, "w") as f:
         f.write(f"# ncu summary: {rep}\n\n{note}\n\n`ncu --set full --clock-control none --import-source on` "
