@@ -302,6 +302,10 @@ int32_t aule_set_kernel_path(int32_t path) {
     g_engine.set_kernel_path(path);
     return 0;
 }
+int32_t aule_set_trace_buffer(uint64_t dptr) {
+    g_engine.set_trace_buffer(dptr);
+    return 0;
+}
 int32_t aule_smoke_multiply(const float* in, float* out, uint32_t n) {
     if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
     std::string e = g_engine.smoke_multiply(primary_device(), in, out, n);

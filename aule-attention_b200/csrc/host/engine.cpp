@@ -338,21 +338,22 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             if (e.empty()) e = make_tmap(&tmdK, dtype, dk, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
             if (e.empty()) e = make_tmap(&tmdV, dtype, dv, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
             BwdParams bp;
-            bp.dq_out = (void*)dq; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
+            bp.dq_out = (void*)dq; bp.q = (const void*)q; bp.d_o = (const void*)d_o; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
             bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
-            bp.order = bwd_order_;
+            bp.order = bwd_serial_;
+            bp.trace = (unsigned long long*)trace_;
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
-            if (e.empty()) {
+            if (e.empty() && bwd_order_ != 2) {                 // (timing hook: 2 = dQ kernel only)
                 void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
                 snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
                 e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, (unsigned)BwdCfg<128>::THREADS,
                            d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
             }
-            if (e.empty()) {
-                void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &bp};
+            if (e.empty() && bwd_order_ != 1) {                 // (timing hook: 1 = dK/dV kernel only)
+                void* params[] = {&tmK, &tmV, &bp};
                 snprintf(name, sizeof(name), "aule_bwd_dq_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
                 e = launch(d, d.bwd_dq_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas_dq, 1, 1,
                            (unsigned)aule_kp::BwdDqCfg<128>::THREADS,

@@ -10,7 +10,7 @@
 //   * dK/dV kernel (bwd_dkv_body): one CTA per (KV block of 128 keys, kv head, batch); K_j, V_j resident in SMEM;
 //     dV [256,384) and dK [384,512) accumulate in TMEM over every q-head of the GQA group and every query block;
 //   * dQ kernel (bwd_dq_body): one CTA per (query block of 128 rows, q head, batch); Q_i, dO_i resident, K_j/V_j
-//     stream through a 2-stage ring, dQ accumulates in TMEM.  S, P and dS are recomputed there (two extra GEMMs and
+//     stream through a 2-stage ring, dS stays in TMEM (TS MMA), dQ accumulates in TMEM.  S, P and dS are recomputed there (two extra GEMMs and
 //     one extra exp pass) -- measured faster than reducing dQ partials through 4.4 GB of fp32 red.global.add per
 //     config-C/2 launch (experiments/attn_bwd_sm100_v2_fused_atomics.cu.txt), and deterministic.
 // Both are 544-thread CTAs (four compute warps per scheduler hide the TMEM-load / MUFU / barrier latencies):
@@ -34,6 +34,17 @@ namespace bwd100 {
 using namespace sm100;
 using aule_kp::BwdParams;
 template <int D> using Cfg = aule_kp::BwdCfg<D>;
+
+// Bring-up tracer (aule_set_trace_buffer): CTA 0 only, one region of 4096 entries per traced thread.
+struct Tracer {
+    unsigned long long* buf;
+    uint32_t n;
+    __device__ __forceinline__ Tracer(unsigned long long* base, uint32_t region, bool on)
+        : buf((base && on && blockIdx.x == 0) ? base + region * 4096 : nullptr), n(0) {}
+    __device__ __forceinline__ void ev(uint32_t code, uint32_t step) {
+        if (buf && n < 4096) buf[n++] = ((unsigned long long)((code << 8) | (step & 255u)) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    }
+};
 
 // P phase for 32 columns of one row: exp2(S*c - lse2), masked when the block touches the diagonal / the ragged ends.
 template <bool MASK>
@@ -76,12 +87,13 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     const uint32_t bar_kv = sb + C::OFF_BAR;        // K_j, V_j landed (once)
     const uint32_t bar_q0 = bar_kv + 8;             // Q buffer 0 / 1 landed (+8)
     const uint32_t bar_do = bar_kv + 24;            // dO landed
-    const uint32_t bar_s = bar_kv + 32;             // S(i) complete (commit)
-    const uint32_t bar_dp = bar_kv + 40;            // dP(i) complete (commit)
-    const uint32_t bar_p = bar_kv + 48;             // compute -> issuer: P(i) in SMEM, S columns consumed (512 arrivals)
-    const uint32_t bar_ds = bar_kv + 56;            // compute -> issuer: dS(i) in SMEM, dP columns consumed (512 arrivals)
-    const uint32_t bar_dv = bar_kv + 64;            // dV(i) complete (commit): P buffer and dO buffer free
-    const uint32_t bar_dk = bar_kv + 72;            // dK(i) complete (commit): dS buffer and Q buffer i&1 free
+    const uint32_t bar_s0 = bar_kv + 32;            // S(i) complete in buffer i&1 (commit) (+8 for odd i)
+    const uint32_t bar_dp0 = bar_kv + 48;           // dP(i) complete in buffer i&1 (commit) (+8 for odd i)
+    const uint32_t bar_p = bar_kv + 64;             // compute -> issuer: P(i) in SMEM (one arrival per compute warp)
+    const uint32_t bar_ds = bar_kv + 72;            // compute -> issuer: dS(i) in SMEM, buffer i&1 consumed (16 arrivals)
+    const uint32_t bar_dv = bar_kv + 80;            // dV(i) complete (commit): P buffer and dO buffer free
+    const uint32_t bar_dk = bar_kv + 88;            // dK(i) complete (commit): dS buffer and Q buffer i&1 free
+    const uint32_t bar_sfree = bar_kv + 96;         // compute -> issuer: S(i) copied to registers, its buffer may take dP(i) (16 arrivals)
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
     const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO = sb + C::OFF_DO,
                    sP = sb + C::OFF_P, sdS = sb + C::OFF_DS;
@@ -89,7 +101,8 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     if (threadIdx.x == 0) {
         if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
         mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1); mbar_init(bar_do, 1);
-        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 512); mbar_init(bar_ds, 512);
+        mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_dp0, 1); mbar_init(bar_dp0 + 8, 1);
+        mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_sfree, 16);    // one arrival per compute warp
         mbar_init(bar_dv, 1); mbar_init(bar_dk, 1);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
@@ -99,7 +112,9 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 384;
+    // S(i) and dP(i) share buffer i&1 (columns [0,128) / [128,256)): S(i) is dead once the compute warps hold it in
+    // registers, so dP(i) lands in the same columns while S(i+1) is already waiting in the other buffer.
+    constexpr uint32_t COL_DV = 256, COL_DK = 384;
 
     // ---- which KV block
     const uint32_t per = p.Hkv * p.B;
@@ -127,7 +142,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 const uint32_t g = step / steps_per_head, i = i_begin + (step - g * steps_per_head);
                 row = (int32_t)(i * 128);
                 bh = (int32_t)(b * p.Hq + hk * group + g);
-            };
+            };                                                               // (issuer thread only: one division per load)
             auto load_q = [&](uint32_t step) {
                 int32_t row, bh; coords(step, row, bh);
                 const uint32_t bar = bar_q0 + 8 * (step & 1), dst = sQ0 + (step & 1) * C::TILE_BYTES;
@@ -146,9 +161,9 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
-                    mma_ss(tmem + COL_S, mk(HI_K_HI, (HI_K_LO | (sQ >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), ID_KK, kk > 0);
+                    mma_ss(tmem + 128 * (step & 1), mk(HI_K_HI, (HI_K_LO | (sQ >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), ID_KK, kk > 0);
                 }
-                mma_commit(bar_s);
+                mma_commit(bar_s0 + 8 * (step & 1));
             };
             auto issue_dk = [&](uint32_t step) {                             // dK += dS^T Q   (K = 128 query rows)
                 const uint32_t sQ = sQ0 + (step & 1) * C::TILE_BYTES;
@@ -164,54 +179,69 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 tma_load_3d(sK + c * C::CHUNK_BYTES, tmK, bar_kv, c * 64, (int32_t)key0, (int32_t)bhk);
                 tma_load_3d(sV + c * C::CHUNK_BYTES, tmV, bar_kv, c * 64, (int32_t)key0, (int32_t)bhk);
             }
-            if (nsteps > 0) { load_q(0); load_do(0); }
-            if (nsteps > 1) load_q(1);
-            mbar_wait(bar_kv, 0);
+            Tracer tr(p.trace, 0, true);
+            // ---- loads, issued from the wait loops as soon as their buffer is released:
+            //   Q(s)  -> buffer s&1 once dK(s-2) has read it;   dO(s) -> the single dO buffer once dV(s-1) has read it.
+            uint32_t ql = 0, dl = 0;
+            auto pump = [&]() {
+                if (ql < nsteps && (ql < 2 || mbar_try_wait<0>(bar_dk, (ql - 2) & 1))) { load_q(ql); ++ql; }
+                if (dl < nsteps && (dl < 1 || mbar_try_wait<0>(bar_dv, (dl - 1) & 1))) { load_do(dl); ++dl; }
+            };
+            auto wait = [&](uint32_t bar, uint32_t parity) {
+                while (!mbar_try_wait<0>(bar, parity)) pump();
+            };
+            pump(); pump();
+            wait(bar_kv, 0);
             if (nsteps > 0) {
-                mbar_wait(bar_q0, 0);
+                wait(bar_q0, 0);
                 tc_fence_after();
                 issue_s(0);
             }
+            // Steady state, per step i (tensor pipe order == readiness order):
+            //   dK(i-1)  [dS(i-1) ready]          -> releases Q buffer (i+1)&1 -> TMA Q(i+1)
+            //   dP(i)    [S(i) in registers]      -> buffer i&1
+            //   S(i+1)   [Q(i+1) landed]          -> buffer (i+1)&1 (its dP(i-1) was consumed with dS(i-1))
+            //   dV(i)    [P(i) ready]             -> releases the dO buffer -> TMA dO(i+1)
             for (uint32_t step = 0; step < nsteps; ++step) {
-                // ---- P phase of step: dK(step-1), dP(step)
                 if (step > 0) {
-                    mbar_wait(bar_ds, (step - 1) & 1);                       // dS(step-1) written, dP columns consumed
+                    wait(bar_ds, (step - 1) & 1);                            // dS(step-1) written, buffer (step-1)&1 consumed
                     tc_fence_after();
+                    tr.ev(13, step);
                     issue_dk(step - 1);
                 }
-                mbar_wait(bar_do, step & 1);
+                tr.ev(10, step);
+                wait(bar_sfree, step & 1);                                   // S(step) is in registers
+                tr.ev(11, step);
+                wait(bar_do, step & 1);
+                tr.ev(12, step);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {                        // dP = dO V^T
                     const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
-                    mma_ss(tmem + COL_DP, mk(HI_K_HI, (HI_K_LO | (sdO >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), ID_KK, kk > 0);
+                    mma_ss(tmem + 128 * (step & 1), mk(HI_K_HI, (HI_K_LO | (sdO >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), ID_KK, kk > 0);
                 }
-                mma_commit(bar_dp);
-                if (step > 0 && step + 1 < nsteps) {
-                    mbar_wait(bar_dk, (step - 1) & 1);                       // Q buffer (step+1)&1 released by dK(step-1)
-                    load_q(step + 1);
+                mma_commit(bar_dp0 + 8 * (step & 1));
+                if (step + 1 < nsteps) {
+                    wait(bar_q0 + 8 * ((step + 1) & 1), ((step + 1) >> 1) & 1);   // (Q(step+1) is requested by pump once dK(step-1) is done)
+                    tc_fence_after();
+                    tr.ev(14, step);
+                    issue_s(step + 1);
                 }
-                // ---- dS phase of step: dV(step), S(step+1)
-                mbar_wait(bar_p, step & 1);                                  // P(step) written, S columns consumed
+                tr.ev(17, step);
+                wait(bar_p, step & 1);                                       // P(step) written
+                tr.ev(18, step);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)                               // dV += P^T dO   (K = 128 query rows)
                     mma_ss(tmem + COL_DV, mk(HI_MN_HI, (HI_MN_LO | (sP >> 4)) + kk * 128), mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128),
                            ID_MNMN, (step > 0 || kk > 0) ? 1u : 0u);
                 mma_commit(bar_dv);
-                if (step + 1 < nsteps) {
-                    mbar_wait(bar_q0 + 8 * ((step + 1) & 1), ((step + 1) >> 1) & 1);
-                    tc_fence_after();
-                    issue_s(step + 1);
-                    mbar_wait(bar_dv, step & 1);                             // dO buffer released by dV(step)
-                    load_do(step + 1);
-                }
             }
             if (nsteps > 0) {
-                mbar_wait(bar_ds, (nsteps - 1) & 1);
+                wait(bar_ds, (nsteps - 1) & 1);
                 tc_fence_after();
                 issue_dk(nsteps - 1);
-                mbar_wait(bar_dk, (nsteps - 1) & 1);                         // every MMA complete
+                wait(bar_dk, (nsteps - 1) & 1);                              // every MMA complete
             }
         }
     } else {
@@ -219,58 +249,77 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
         const uint32_t qt = warp >> 2;                               // key quarter: columns [32qt, 32qt+32)
         const uint32_t r = (warp & 3) * 32 + lane;                   // row of the tile == TMEM lane
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
-        // row statistics of the NEXT step are fetched one step ahead and only touched one step later
+        // row statistics of the NEXT step are fetched one step ahead and only touched one step later;
+        // (g, i) = (q-head of the group, query block) advance without a division
         float lse_n = 0.f, delta_n = 0.f;
-        auto fetch_stats = [&](uint32_t step) {
-            const uint32_t g = step / steps_per_head, i = i_begin + (step - g * steps_per_head);
-            const uint32_t row = i * 128 + r;
-            const size_t off = ((size_t)b * p.Hq + hk * group + g) * p.Sq;
+        uint32_t g_n = 0, i_n = i_begin;                             // coordinates of the step being prefetched
+        auto fetch_stats = [&]() {
+            const uint32_t row = i_n * 128 + r;
+            const size_t off = ((size_t)b * p.Hq + hk * group + g_n) * p.Sq;
             const bool ok = row < p.Sq;
             lse_n = ok ? p.lse[off + row] : 0.f;
             delta_n = ok ? p.delta[off + row] : 0.f;
+            if (++i_n == nqb) { i_n = i_begin; ++g_n; }
         };
-        if (nsteps > 0) fetch_stats(0);
+        if (nsteps > 0) fetch_stats();
+        Tracer tr(p.trace, 1 + (qt & 1), (warp == 0 || warp == 4) && lane == 0);
+        uint32_t i = i_begin;                                        // query block of the current step
         for (uint32_t step = 0; step < nsteps; ++step) {
-            const uint32_t g = step / steps_per_head, i = i_begin + (step - g * steps_per_head);
             const uint32_t row = i * 128 + r;                        // global query row of this thread
             const bool row_ok = row < p.Sq;
             const float lse2 = lse_n * 1.4426950408889634f, delta = delta_n;
-            if (step + 1 < nsteps) fetch_stats(step + 1);
+            if (step + 1 < nsteps) fetch_stats();
             const bool diag = p.causal && (i * 128 < key0 + 128);    // block touches the diagonal
             const bool masked = diag || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
+            if (++i == nqb) i = i_begin;
 
             // ---- P phase: P = exp2(S*scale_log2 - LSE*log2e) (fp32, kept in registers) -> 16-bit -> swizzled SMEM
             float pv[32];
-            mbar_wait(bar_s, step & 1);
+            const uint32_t tbuf = tmem + lane_addr + 128 * (step & 1) + 32 * qt;
+            tr.ev(20, step);
+            mbar_wait(bar_s0 + 8 * (step & 1), (step >> 1) & 1);
+            tr.ev(21, step);
             tc_fence_after();
             {
                 uint32_t s[32];
-                tmem_ld32(tmem + lane_addr + COL_S + 32 * qt, s);
+                tmem_ld32(tbuf, s);
                 tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sfree);               // the buffer may take dP(step)
+                tr.ev(22, step);
                 if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
                 else p_from_s<false>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
             }
+            tr.ev(28, step);
             if (step > 0) mbar_wait(bar_dv, (step - 1) & 1);         // dV(step-1) has read the P buffer
             store_row32<BF16>(sP + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();                                // generic-proxy writes -> visible to the MMA (async proxy)
             tc_fence_before();
-            mbar_arrive(bar_p);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p);
+            tr.ev(23, step);
 
             // ---- dS phase: dS = P o (dP - Delta) -> 16-bit -> swizzled SMEM
-            mbar_wait(bar_dp, step & 1);
+            mbar_wait(bar_dp0 + 8 * (step & 1), (step >> 1) & 1);
+            tr.ev(24, step);
             tc_fence_after();
             {
                 uint32_t dp[32];
-                tmem_ld32(tmem + lane_addr + COL_DP + 32 * qt, dp);
+                tmem_ld32(tbuf, dp);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 32; ++e) pv[e] *= (__uint_as_float(dp[e]) - delta);
             }
+            tr.ev(25, step);
             if (step > 0) mbar_wait(bar_dk, (step - 1) & 1);         // dK(step-1) has read the dS buffer
+            tr.ev(26, step);
             store_row32<BF16>(sdS + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_ds);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ds);
+            tr.ev(27, step);
         }
     }
 
@@ -328,37 +377,54 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
 
 // =====================================================================================================
 // dQ kernel: one CTA per (query block of 128 rows, q head, batch), heaviest (last block) first.
-// TMEM: S ping [0,128) / pong [384,512), dP [128,256), dQ [256,256+D).
+// Every MMA is a TS MMA (A operand in TMEM), so a 128x128x16 step reads 4 KB of shared memory instead of the 8 KB
+// (= the whole 128 B/clk) an SS step needs -- measured: the SS forms of S and dP took ~900 cycles per 128^3 GEMM
+// instead of 512 (tools/bwd_trace.py):
+//   Q_i, dO_i      : global -> registers -> TMEM once per CTA (A operands of S = Q K^T and dP = dO V^T)
+//   dS(j)          : written in place over the dP(j) columns the same thread has just read (A operand of dQ += dS K)
+// TMEM: Q [0,64) | dO [64,128) | S/dP/dS buffer 0 [128,256) / 1 [256,384) | dQ [384,384+D).
+//   buffer j&1 holds S(j), then dP(j) (issued once the compute warps hold S(j) in registers), then dS(j) in columns
+//   32q+[0,16) (q = key quarter); dQ(j) precedes S(j+2) in the tensor pipe, so the buffer is recycled without a wait.
+// SMEM: K ring 4 stages (K_j lives from S(j) to dQ(j)) | V ring 3 stages (V_j is dead after dP(j)); the loads are
+// issued from the issuer's wait loops as soon as a stage is released.
+// Tensor-pipe order per step j:  dQ(j-1)  dP(j)  S(j+1).
 template <int D, bool BF16>
-__device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
-                                            const CUtensorMap* tmdO, const BwdParams& p) {
+__device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmK, const CUtensorMap* tmV, const BwdParams& p) {
     using C = aule_kp::BwdDqCfg<D>;
+    constexpr int NK = C::NK, NV = C::NV;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sb = smem_u32(smem);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_qdo = sb + C::OFF_BAR;       // Q_i, dO_i landed (once)
-    const uint32_t bar_kv0 = bar_qdo + 8;           // K/V stage 0 / 1 landed (+8)
-    const uint32_t bar_kve0 = bar_qdo + 24;         // dQ(j) complete (commit): K/V stage j&1 and the dS buffer free (+8 for odd j)
-    const uint32_t bar_s0 = bar_qdo + 40;           // S buffer 0 / 1 complete (commit) (+8)
-    const uint32_t bar_dp = bar_qdo + 56;           // dP complete (commit)
-    const uint32_t bar_ds = bar_qdo + 64;           // compute -> issuer: dS in SMEM, S and dP consumed (512 arrivals)
-    const uint32_t bar_done = bar_qdo + 72;         // every MMA complete (commit)
+    const uint32_t bar_qdo = sb + C::OFF_BAR;       // compute -> issuer: Q_i, dO_i are in TMEM (one arrival per compute warp)
+    const uint32_t bar_kfull0 = bar_qdo + 8;        // K stage s landed (+8s)
+    const uint32_t bar_kfree0 = bar_kfull0 + 8 * NK;   // dQ(j) complete (commit): K stage j%NK free (+8s)
+    const uint32_t bar_vfull0 = bar_kfree0 + 8 * NK;   // V stage s landed (+8s)
+    const uint32_t bar_vfree0 = bar_vfull0 + 8 * NV;   // dP(j) complete (commit): V stage j%NV free (+8s)
+    const uint32_t bar_s0 = bar_vfree0 + 8 * NV;    // S(j) complete in buffer j&1 (commit) (+8)
+    const uint32_t bar_dp0 = bar_s0 + 16;           // dP(j) complete in buffer j&1 (commit) (+8)
+    const uint32_t bar_ds = bar_dp0 + 16;           // compute -> issuer: dS(j) in TMEM (16 arrivals)
+    const uint32_t bar_sfree = bar_ds + 8;          // compute -> issuer: S(j) in registers, its buffer may take dP(j) (16)
+    const uint32_t bar_done = bar_sfree + 8;        // every MMA complete (commit)
+    static_assert(8 * (1 + 2 * NK + 2 * NV + 4 + 3) <= C::BAR_BYTES, "barrier area too small");
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
-    const uint32_t sQ = sb + C::OFF_Q, sdO = sb + C::OFF_DO, sK0 = sb + C::OFF_K, sV0 = sb + C::OFF_V, sdS = sb + C::OFF_DS;
+    const uint32_t sK0 = sb + C::OFF_K, sV0 = sb + C::OFF_V;
 
     if (threadIdx.x == 0) {
         if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
-        mbar_init(bar_qdo, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv0 + 8, 1); mbar_init(bar_kve0, 1); mbar_init(bar_kve0 + 8, 1);
-        mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 512); mbar_init(bar_done, 1);
+        mbar_init(bar_qdo, 16);
+        for (int i = 0; i < NK; ++i) { mbar_init(bar_kfull0 + 8 * i, 1); mbar_init(bar_kfree0 + 8 * i, 1); }
+        for (int i = 0; i < NV; ++i) { mbar_init(bar_vfull0 + 8 * i, 1); mbar_init(bar_vfree0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s0 + 8 * i, 1); mbar_init(bar_dp0 + 8 * i, 1); }
+        mbar_init(bar_ds, 16); mbar_init(bar_sfree, 16); mbar_init(bar_done, 1);
         fence_mbar_init();
-        tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
+        tma_prefetch_desc(tmK); tma_prefetch_desc(tmV);
     }
     if (warp == 16) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_DP = 128, COL_DQ = 256;                   // S buffers at columns 0 and 384
+    constexpr uint32_t COL_Q = 0, COL_DO = 64, COL_BUF = 128, COL_DQ = 384;
 
     // ---- which query block (last = heaviest under causal first)
     const uint32_t per = p.Hq * p.B;
@@ -380,72 +446,97 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
             auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
             constexpr uint32_t ID_KK = instr_desc_f16(BF16, 128, 128, false);
             constexpr uint32_t ID_KMN = instr_desc_f16(BF16, 128, D, true);
-            auto load_kv = [&](uint32_t j) {
-                const uint32_t st = j & 1, bar = bar_kv0 + 8 * st;
-                mbar_expect_tx(bar, 2 * C::TILE_BYTES);
+            Tracer tr(p.trace, 0, true);
+            // ---- loads: K(jj) -> stage jj%NK once dQ(jj-NK) has released it, V(jj) -> stage jj%NV once dP(jj-NV) has.
+            uint32_t kl = 0, kl_st = 0, kl_use = 0;                           // next K load, its stage, earlier fills of that stage
+            uint32_t vl = 0, vl_st = 0, vl_use = 0;
+            auto pump = [&]() {
+                if (kl < n && (kl_use == 0 || mbar_try_wait<0>(bar_kfree0 + 8 * kl_st, (kl_use - 1) & 1))) {
+                    const uint32_t bar = bar_kfull0 + 8 * kl_st;
+                    mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
-                for (int c = 0; c < C::CHUNKS; ++c) {
-                    tma_load_3d(sK0 + st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmK, bar, c * 64, (int32_t)(j * 128), (int32_t)bkv);
-                    tma_load_3d(sV0 + st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmV, bar, c * 64, (int32_t)(j * 128), (int32_t)bkv);
+                    for (int c = 0; c < C::CHUNKS; ++c)
+                        tma_load_3d(sK0 + kl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmK, bar, c * 64, (int32_t)(kl * 128), (int32_t)bkv);
+                    ++kl;
+                    if (++kl_st == NK) { kl_st = 0; ++kl_use; }
+                }
+                if (vl < n && (vl_use == 0 || mbar_try_wait<0>(bar_vfree0 + 8 * vl_st, (vl_use - 1) & 1))) {
+                    const uint32_t bar = bar_vfull0 + 8 * vl_st;
+                    mbar_expect_tx(bar, C::TILE_BYTES);
+#pragma unroll
+                    for (int c = 0; c < C::CHUNKS; ++c)
+                        tma_load_3d(sV0 + vl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmV, bar, c * 64, (int32_t)(vl * 128), (int32_t)bkv);
+                    ++vl;
+                    if (++vl_st == NV) { vl_st = 0; ++vl_use; }
                 }
             };
-            auto issue_s = [&](uint32_t j) {                                 // S = Q K_j^T into S buffer j&1
-                const uint32_t sK = sK0 + (j & 1) * C::TILE_BYTES;
+            auto wait = [&](uint32_t bar, uint32_t parity) {                 // blocking wait that keeps the loads flowing
+                while (!mbar_try_wait<0>(bar, parity)) pump();
+            };
+            auto issue_s = [&](uint32_t j, uint32_t kst) {                   // S = Q K_j^T into buffer j&1 (A = Q in TMEM)
+                const uint32_t sK = sK0 + kst * C::TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
-                    mma_ss(tmem + 384 * (j & 1), mk(HI_K_HI, (HI_K_LO | (sQ >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), ID_KK, kk > 0);
+                    mma_ts(tmem + COL_BUF + 128 * (j & 1), tmem + COL_Q + kk * 8, mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), ID_KK, kk > 0);
                 }
                 mma_commit(bar_s0 + 8 * (j & 1));
             };
-            auto issue_dq = [&](uint32_t j) {                                // dQ += dS K_j   (K = 128 keys)
-                const uint32_t sK = sK0 + (j & 1) * C::TILE_BYTES;
+            auto issue_dq = [&](uint32_t j, uint32_t kst) {                  // dQ += dS K_j (K = 128 keys, A = dS(j) inside buffer j&1)
+                const uint32_t sK = sK0 + kst * C::TILE_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
-                    mma_ss(tmem + COL_DQ, mk(HI_K_HI, (HI_K_LO | (sdS >> 4)) + off), mk(HI_MN_HI, (HI_MN_LO | (sK >> 4)) + kk * 128), ID_KMN,
-                           (j > 0 || kk > 0) ? 1u : 0u);
-                }
+                for (int kk = 0; kk < 8; ++kk)
+                    mma_ts(tmem + COL_DQ, tmem + COL_BUF + 128 * (j & 1) + 32 * (kk >> 1) + 8 * (kk & 1),
+                           mk(HI_MN_HI, (HI_MN_LO | (sK >> 4)) + kk * 128), ID_KMN, (j > 0 || kk > 0) ? 1u : 0u);
+                mma_commit(bar_kfree0 + 8 * kst);
             };
-            mbar_expect_tx(bar_qdo, 2 * C::TILE_BYTES);
-#pragma unroll
-            for (int c = 0; c < C::CHUNKS; ++c) {
-                tma_load_3d(sQ + c * C::CHUNK_BYTES, tmQ, bar_qdo, c * 64, (int32_t)(i * 128), (int32_t)bh);
-                tma_load_3d(sdO + c * C::CHUNK_BYTES, tmdO, bar_qdo, c * 64, (int32_t)(i * 128), (int32_t)bh);
-            }
-            load_kv(0);
-            if (n > 1) load_kv(1);
-            mbar_wait(bar_qdo, 0);
-            mbar_wait(bar_kv0, 0);
+            for (int t = 0; t < NK; ++t) pump();                             // fill both rings
+            wait(bar_qdo, 0);
+            wait(bar_kfull0, 0);
             tc_fence_after();
-            issue_s(0);
+            issue_s(0, 0);
+            uint32_t ks = 0, kp = 0, vs = 0, vp = 0;                          // K / V stage of step j and the parity of its fill
             for (uint32_t j = 0; j < n; ++j) {
-                const uint32_t sV = sV0 + (j & 1) * C::TILE_BYTES;
+                const uint32_t ks_prev = (ks == 0) ? NK - 1 : ks - 1;                                         // of step j-1
+                const uint32_t ks_next = (ks == NK - 1) ? 0 : ks + 1, kp_next = (ks == NK - 1) ? (kp ^ 1) : kp;   // of step j+1
                 if (j > 0) {
-                    mbar_wait(bar_ds, (j - 1) & 1);                          // dS(j-1) written; S(j-1), dP(j-1) consumed
+                    wait(bar_ds, (j - 1) & 1);                               // dS(j-1) in TMEM
                     tc_fence_after();
-                    issue_dq(j - 1);
-                    mma_commit(bar_kve0 + 8 * ((j - 1) & 1));
+                    tr.ev(13, j);
+                    issue_dq(j - 1, ks_prev);
+                    if (p.order & 1) { wait(bar_kfree0 + 8 * ks_prev, (ks == 0) ? (kp ^ 1) : kp); tr.ev(30, j); }
                 }
+                tr.ev(10, j);
+                wait(bar_sfree, j & 1);                                      // S(j) is in registers
+                tr.ev(11, j);
+                wait(bar_vfull0 + 8 * vs, vp);
+                tr.ev(12, j);
+                tc_fence_after();
+                {
+                    const uint32_t sV = sV0 + vs * C::TILE_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {                        // dP = dO V_j^T (V_j landed with K_j)
-                    const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
-                    mma_ss(tmem + COL_DP, mk(HI_K_HI, (HI_K_LO | (sdO >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), ID_KK, kk > 0);
-                }
-                mma_commit(bar_dp);
-                if (j + 1 < n) {
-                    if (j > 0) {
-                        mbar_wait(bar_kve0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);   // stage (j+1)&1 released by dQ(j-1)
-                        load_kv(j + 1);
+                    for (int kk = 0; kk < D / 16; ++kk) {                    // dP = dO V_j^T -> buffer j&1 (A = dO in TMEM)
+                        const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
+                        mma_ts(tmem + COL_BUF + 128 * (j & 1), tmem + COL_DO + kk * 8, mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), ID_KK, kk > 0);
                     }
-                    mbar_wait(bar_kv0 + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
-                    tc_fence_after();
-                    issue_s(j + 1);                                          // its buffer was read in the P phase of j-1
+                    mma_commit(bar_dp0 + 8 * (j & 1));
+                    mma_commit(bar_vfree0 + 8 * vs);
+                    if (p.order & 1) { tr.ev(31, j); wait(bar_dp0 + 8 * (j & 1), (j >> 1) & 1); tr.ev(32, j); }
                 }
+                if (j + 1 < n) {
+                    wait(bar_kfull0 + 8 * ks_next, kp_next);
+                    tc_fence_after();
+                    tr.ev(14, j);
+                    issue_s(j + 1, ks_next);                                 // buffer (j+1)&1: follows dQ(j-1) in the tensor pipe
+                    if (p.order & 1) { tr.ev(33, j); wait(bar_s0 + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1); tr.ev(34, j); }
+                }
+                tr.ev(15, j);
+                ks = ks_next; kp = kp_next;
+                if (++vs == NV) { vs = 0; vp ^= 1; }
             }
-            mbar_wait(bar_ds, (n - 1) & 1);
+            wait(bar_ds, (n - 1) & 1);
             tc_fence_after();
-            issue_dq(n - 1);
+            issue_dq(n - 1, (n - 1) % NK);
             mma_commit(bar_done);
         }
     } else {
@@ -457,61 +548,101 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
         const uint32_t row = i * 128 + r;
         const size_t stat_off = (size_t)bh * p.Sq;
         const bool row_ok = row < p.Sq;
+        // ---- Q_i, dO_i: this thread's D/4 elements of its row -> TMEM (A operands), zero beyond Sq
+        {
+            constexpr int NR = D / 8;                                // 32-bit registers per thread and tensor
+            uint32_t a[NR], g[NR];
+            const size_t eoff = ((stat_off + (row_ok ? row : 0)) * D + (D / 4) * qt) * 2;
+            const uint4* gq = reinterpret_cast<const uint4*>(static_cast<const char*>(p.q) + eoff);
+            const uint4* gd = reinterpret_cast<const uint4*>(static_cast<const char*>(p.d_o) + eoff);
+#pragma unroll
+            for (int u = 0; u < NR / 4; ++u) {
+                const uint4 x = row_ok ? gq[u] : make_uint4(0, 0, 0, 0);
+                const uint4 y = row_ok ? gd[u] : make_uint4(0, 0, 0, 0);
+                a[4 * u] = x.x; a[4 * u + 1] = x.y; a[4 * u + 2] = x.z; a[4 * u + 3] = x.w;
+                g[4 * u] = y.x; g[4 * u + 1] = y.y; g[4 * u + 2] = y.z; g[4 * u + 3] = y.w;
+            }
+            if constexpr (NR == 16) {
+                tmem_st16(tmem + lane_addr + COL_Q + NR * qt, a);
+                tmem_st16(tmem + lane_addr + COL_DO + NR * qt, g);
+            } else {
+                tmem_st8(tmem + lane_addr + COL_Q + NR * qt, a);
+                tmem_st8(tmem + lane_addr + COL_DO + NR * qt, g);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_qdo);
+        }
         const float lse2 = row_ok ? p.lse[stat_off + row] * 1.4426950408889634f : 0.f;
         const float delta = row_ok ? p.delta[stat_off + row] : 0.f;
+        Tracer tr(p.trace, 1 + (qt & 1), (warp == 0 || warp == 4) && lane == 0);
         for (uint32_t j = 0; j < n; ++j) {
             const uint32_t key0 = j * 128;
             const bool diag = p.causal && (i * 128 < key0 + 128);
             const bool masked = diag || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
+            const uint32_t tbuf = tmem + lane_addr + COL_BUF + 128 * (j & 1) + 32 * qt;
             // ---- P phase
             float pv[32];
+            tr.ev(20, j);
             mbar_wait(bar_s0 + 8 * (j & 1), (j >> 1) & 1);
+            tr.ev(21, j);
             tc_fence_after();
             {
                 uint32_t s[32];
-                tmem_ld32(tmem + lane_addr + 384 * (j & 1) + 32 * qt, s);
+                tmem_ld32(tbuf, s);
                 tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sfree);               // one arrival per warp: the buffer may take dP(j)
+                tr.ev(22, j);
                 if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
                 else p_from_s<false>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
             }
-            // ---- dS phase
-            mbar_wait(bar_dp, j & 1);
+            // ---- dS phase: dS = P o (dP - Delta) -> 16-bit, in place over the first 16 of this thread's 32 dP columns
+            tr.ev(23, j);
+            mbar_wait(bar_dp0 + 8 * (j & 1), (j >> 1) & 1);
+            tr.ev(24, j);
             tc_fence_after();
+            uint32_t pk[16];
             {
                 uint32_t dp[32];
-                tmem_ld32(tmem + lane_addr + COL_DP + 32 * qt, dp);
+                tmem_ld32(tbuf, dp);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) pv[e] *= (__uint_as_float(dp[e]) - delta);
+                for (int e = 0; e < 16; ++e)
+                    pk[e] = pack2<BF16>(pv[2 * e] * (__uint_as_float(dp[2 * e]) - delta), pv[2 * e + 1] * (__uint_as_float(dp[2 * e + 1]) - delta));
             }
-            if (j > 0) mbar_wait(bar_kve0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);   // dQ(j-1) has read the dS buffer
-            store_row32<BF16>(sdS + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
-            fence_proxy_async_smem();
+            tr.ev(25, j);
+            tmem_st16(tbuf, pk);
+            tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_ds);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ds);
+            tr.ev(27, j);
         }
         // ---- epilogue: dQ (x scale) -> 16-bit -> global (this half's D/2 columns of the row: 64 or 128 contiguous bytes)
         mbar_wait(bar_done, 0);
         tc_fence_after();
         if (warp < 8) {
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.dq_out) + ((stat_off + (row_ok ? row : 0)) * D + (D / 2) * h) * 2);
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.dq_out) + ((stat_off + (row_ok ? row : 0)) * D + (D / 2) * h) * 2);
 #pragma unroll 1
-        for (int c = 0; c < D / 64; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem + lane_addr + COL_DQ + (D / 2) * h + c * 32, o);
-            tmem_wait_ld();
-            if (row_ok) {
+            for (int c = 0; c < D / 64; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tmem + lane_addr + COL_DQ + (D / 2) * h + c * 32, o);
+                tmem_wait_ld();
+                if (row_ok) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 v;
-                    v.x = pack2<BF16>(__uint_as_float(o[8 * u + 0]) * p.scale, __uint_as_float(o[8 * u + 1]) * p.scale);
-                    v.y = pack2<BF16>(__uint_as_float(o[8 * u + 2]) * p.scale, __uint_as_float(o[8 * u + 3]) * p.scale);
-                    v.z = pack2<BF16>(__uint_as_float(o[8 * u + 4]) * p.scale, __uint_as_float(o[8 * u + 5]) * p.scale);
-                    v.w = pack2<BF16>(__uint_as_float(o[8 * u + 6]) * p.scale, __uint_as_float(o[8 * u + 7]) * p.scale);
-                    dst[c * 4 + u] = v;
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 v;
+                        v.x = pack2<BF16>(__uint_as_float(o[8 * u + 0]) * p.scale, __uint_as_float(o[8 * u + 1]) * p.scale);
+                        v.y = pack2<BF16>(__uint_as_float(o[8 * u + 2]) * p.scale, __uint_as_float(o[8 * u + 3]) * p.scale);
+                        v.z = pack2<BF16>(__uint_as_float(o[8 * u + 4]) * p.scale, __uint_as_float(o[8 * u + 5]) * p.scale);
+                        v.w = pack2<BF16>(__uint_as_float(o[8 * u + 6]) * p.scale, __uint_as_float(o[8 * u + 7]) * p.scale);
+                        dst[c * 4 + u] = v;
+                    }
                 }
             }
-        }
         }
     }
     tc_fence_before();
@@ -532,12 +663,10 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmQ, const CUtens
         bwd100::bwd_dkv_body<DD, BF>(&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, p);                           \
     }
 #define AULE_BWD100_DQ(NAME, DD, BF)                                                                     \
-    extern "C" __global__ void __launch_bounds__(544, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
-                                                              const __grid_constant__ CUtensorMap tmK,    \
+    extern "C" __global__ void __launch_bounds__(544, 1) NAME(const __grid_constant__ CUtensorMap tmK,    \
                                                               const __grid_constant__ CUtensorMap tmV,    \
-                                                              const __grid_constant__ CUtensorMap tmdO,   \
                                                               const aule_kp::BwdParams p) {               \
-        bwd100::bwd_dq_body<DD, BF>(&tmQ, &tmK, &tmV, &tmdO, p);                                          \
+        bwd100::bwd_dq_body<DD, BF>(&tmK, &tmV, p);                                                       \
     }
 
 AULE_BWD100(aule_bwd_sm100_bf16_d128, 128, true)

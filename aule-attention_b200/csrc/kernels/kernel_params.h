@@ -59,12 +59,15 @@ struct FwdCfg {
 // ---- tcgen05 backward (attn_bwd_sm100.cu) ---------------------------------------------
 struct BwdParams {
     void* dq_out;             // dQ kernel: [B,Hq,Sq,D] output in the input dtype
+    const void* q;            // dQ kernel: Q and dO [B,Hq,Sq,D] are read straight from global memory into TMEM
+    const void* d_o;
     const float* lse;         // [B,Hq,Sq] natural-log LSE of the forward
     const float* delta;       // [B,Hq,Sq] rowsum(O o dO)
     uint32_t B, Hq, Hkv, Sq, Sk;
     float scale, scale_log2;
     int32_t causal;
-    int32_t order;            // MMA issue order (tuning): bit 0: dP(i) before dK(i-1) / dQ(j-1); bit 1: S(i+1) before dV(i)
+    int32_t order;            // reserved for A/B tuning of the MMA issue order (unused by the shipped kernels)
+    unsigned long long* trace; // bring-up: CTA 0 records (tag << 48 | clock64) events here (3 x 4096 entries) or nullptr
 };
 template <int D>
 struct BwdCfg {
@@ -79,24 +82,24 @@ struct BwdCfg {
     static constexpr uint32_t OFF_P = 5 * TILE_BYTES;           // P  [128 q rows][128 keys] 16-bit
     static constexpr uint32_t OFF_DS = OFF_P + 2 * CHUNK_BYTES; // dS same shape
     static constexpr uint32_t OFF_BAR = OFF_DS + 2 * CHUNK_BYTES;
-    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 96;           // 10 mbarriers
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 128;          // 13 mbarriers
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
 };
 
-// dQ kernel (query block outer): Q, dO resident | K,V double-buffered | dS | barriers
+// dQ kernel (query block outer): K ring | V ring | barriers   (Q, dO, dS live in TMEM)
 template <int D>
 struct BwdDqCfg {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
     static constexpr int THREADS = 544;
+    static constexpr int NK = 4, NV = 3;                        // ring stages
     static constexpr int CHUNKS = D / 64;
     static constexpr uint32_t CHUNK_BYTES = 128 * 128;
     static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
-    static constexpr uint32_t OFF_Q = 0, OFF_DO = TILE_BYTES;
-    static constexpr uint32_t OFF_K = 2 * TILE_BYTES;           // 2 stages
-    static constexpr uint32_t OFF_V = 4 * TILE_BYTES;           // 2 stages
-    static constexpr uint32_t OFF_DS = 6 * TILE_BYTES;          // dS [128 q rows][128 keys] 16-bit
-    static constexpr uint32_t OFF_BAR = OFF_DS + 2 * CHUNK_BYTES;
-    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 96;
+    static constexpr uint32_t OFF_K = 0;
+    static constexpr uint32_t OFF_V = NK * TILE_BYTES;
+    static constexpr uint32_t OFF_BAR = (NK + NV) * TILE_BYTES;
+    static constexpr uint32_t BAR_BYTES = 192;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
 };
 

@@ -180,6 +180,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05.mma
 // Shared-memory matrix descriptor (64-bit):
 //   [ 0,14) start address >> 4      [16,30) leading-dim byte offset >> 4

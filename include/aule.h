@@ -186,6 +186,10 @@ AULE_API const char* aule_last_kernel(void);
  * module-load / launch / copy path (the tests/test_multiply.zig analogue,
  * src/compute_pipeline.zig:203-254 + shaders/test.comp). */
 AULE_API int32_t aule_set_kernel_path(int32_t path);
+/* Bring-up hook: a device buffer (>= 3 x 4096 u64, zeroed by the caller) into which CTA 0 of the backward kernels
+ * records (tag << 48 | clock64) events of its issuer thread and of one thread per compute group; 0 disables.
+ * Read by tools/bwd_trace.py to draw the per-step pipeline timeline. */
+AULE_API int32_t aule_set_trace_buffer(uint64_t dptr);
 AULE_API int32_t aule_smoke_multiply(const float* in, float* out, uint32_t n);
 /* Library / ABI version string. */
 AULE_API const char* aule_version(void);

@@ -1,6 +1,7 @@
-"""A/B of the backward kernels' MMA issue orders (BwdParams::order, aule_set_kernel_path bits 10-11) on the GPU box.
-Times aule_attention_backward_dptr directly (no autograd overhead), interleaved rounds, median per order; checks that
-every order returns bit-identical gradients.  usage: python tools/bwd_orders.py [rounds]"""
+"""Backward timing split on the GPU box: aule_attention_backward_dptr called directly (no autograd overhead) with the
+timing hook of aule_set_kernel_path bits 10-11 (0: whole backward, 1: Delta + dK/dV kernel only, 2: Delta + dQ kernel
+only), interleaved rounds, median.  TFLOP/s are always quoted on the whole backward's 2.5x-forward FLOPs, so only the
+mode-0 figure is a throughput; modes 1/2 show where the time goes.  usage: python tools/bwd_orders.py [rounds]"""
 import json
 import os
 import statistics
@@ -14,7 +15,7 @@ from aule import cuda_flash, ffi  # noqa: E402
 
 lib = ffi.ensure_init()
 ROUNDS = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-ORDERS = [int(x) for x in os.environ.get("AULE_BWD_ORDERS", "0,1,2,3").split(",")]
+ORDERS = [int(x) for x in os.environ.get("AULE_BWD_ORDERS", "0,1,2").split(",")]
 
 
 def run(name, B, Hq, Hkv, S, D, reps):
@@ -42,7 +43,7 @@ def run(name, B, Hq, Hkv, S, D, reps):
             lib.aule_set_kernel_path(o_ << 10)
             call()
             torch.cuda.synchronize()
-            if r == 0:
+            if o_ == 0:                                  # the whole backward is bit-reproducible run to run
                 cur = (dq.clone(), dk.clone(), dv.clone())
                 if ref is None:
                     ref = cur
@@ -56,11 +57,12 @@ def run(name, B, Hq, Hkv, S, D, reps):
             torch.cuda.synchronize()
             times[o_].append(e0.elapsed_time(e1) / reps)
     lib.aule_set_kernel_path(0)
-    res = {"config": name, "bit_identical_across_orders": same}
+    res = {"config": name, "bit_identical_run_to_run": same}
     for o_ in ORDERS:
         t = statistics.median(times[o_])
-        res[f"order{o_}_ms"] = round(t, 4)
-        res[f"order{o_}_tflops"] = round(fl / t / 1e9, 1)
+        res[f"mode{o_}_ms"] = round(t, 4)
+        if o_ == 0:
+            res["tflops"] = round(fl / t / 1e9, 1)
     print(json.dumps(res), flush=True)
 
 
