@@ -227,9 +227,20 @@ int32_t aule_attention_forward_gpu(uint64_t qh, uint64_t kh, uint64_t vh, uint64
 }
 
 // ---------------------------------------------------------------- out-of-scope exports (stubs)
-int32_t aule_attention_forward_paged(uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, int32_t, int32_t) {
-    set_error("aule_attention_forward_paged: paged KV cache is outside the B200 hot path (unsupported)");
-    return -10;
+// lib.zig:533-566 -> AttentionEngine.forwardPaged (attention_gpu.zig:484-653): the reference takes ordinary contiguous
+// K/V tensors, copies them into its private 32-token block pool and runs attention over the pool -- the paging is an
+// internal storage detail, the result is aule_attention_forward_gpu's.  Here the same tensors go straight to the
+// fused kernel (no private pool to copy into); error text / code follow lib.zig:561-563.
+int32_t aule_attention_forward_paged(uint64_t q, uint64_t k, uint64_t v, uint64_t output, uint64_t rot_cos,
+                                     uint64_t rot_sin, int32_t causal, int32_t window_size) {
+    int32_t rc = aule_attention_forward_gpu(q, k, v, output, rot_cos, rot_sin, causal, window_size);
+    if (rc == -3) {
+        std::string msg = aule_get_error();
+        const std::string from = "Attention failed";
+        if (msg.compare(0, from.size(), from) == 0) msg = "PagedAttention failed" + msg.substr(from.size());
+        set_error("%s", msg.c_str());
+    }
+    return rc;
 }
 int32_t aule_spatial_sort(uint64_t, uint64_t, uint64_t, uint32_t) {
     set_error("aule_spatial_sort: spatial sort is outside the B200 hot path (unsupported)");
@@ -280,6 +291,19 @@ int32_t aule_rope_dptr(uint64_t x, uint64_t out, uint64_t cos, uint64_t sin, uin
     std::string e = g_engine.rope(device, (CUstream)cu_stream, x, out, cos, sin, (uint64_t)B * H, S, D, dtype,
                                   inverse ? -1.f : 1.f);
     if (!e.empty()) { set_error("RoPE failed: %s", e.c_str()); return -4; }
+    return 0;
+}
+
+int32_t aule_attention_paged_decode_dptr(uint64_t q, uint64_t k_cache, uint64_t v_cache, uint64_t block_tables,
+                                         uint64_t context_lens, uint64_t out, uint32_t B, uint32_t Hq, uint32_t Hkv,
+                                         uint32_t D, uint32_t num_blocks, uint32_t block_size,
+                                         uint32_t max_blocks_per_seq, uint32_t max_context_len, int32_t dtype,
+                                         float scale, int32_t window, int32_t device, uint64_t cu_stream) {
+    if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
+    std::string e = g_engine.paged_decode(device, (CUstream)cu_stream, q, k_cache, v_cache, block_tables, context_lens,
+                                          out, B, Hq, Hkv, D, num_blocks, block_size, max_blocks_per_seq,
+                                          max_context_len, dtype, scale, window);
+    if (!e.empty()) { set_error("PagedAttention failed: %s", e.c_str()); return -4; }
     return 0;
 }
 

@@ -131,6 +131,17 @@ std::string Engine::load_device(int ordinal) {
                           "cuFuncSetAttribute(smem variant)");
         }
     for (int t = 0; t < 3 && e.empty(); ++t) e = get(&d.rope[t], std::string("aule_rope_") + kDtypeSuffix[t]);
+    for (int t = 1; t < 3 && e.empty(); ++t) {
+        e = get(&d.paged[t][0], std::string("aule_paged_sm100_") + kDtypeSuffix[t] + "_d64");
+        if (e.empty()) e = get(&d.paged[t][1], std::string("aule_paged_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty()) e = get(&d.paged_combine[t], std::string("aule_paged_combine_") + kDtypeSuffix[t]);
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.paged[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::PagedCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem paged d64)");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.paged[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::PagedCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem paged d128)");
+    }
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
     if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, 1024 * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
     if (e.empty()) {
@@ -541,6 +552,96 @@ std::string Engine::rope(int dev, CUstream stream, CUdeviceptr x, CUdeviceptr ou
     snprintf(name, sizeof(name), "aule_rope_%s", kDtypeSuffix[dtype]);
     const uint64_t work = rows * (D / 2);
     return launch(d, d.rope[dtype], name, (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)d.sm_count * 16), 1, 1, 256, 0, stream, params);
+}
+
+std::string Engine::make_tmap_paged(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint32_t num_blocks,
+                                    uint32_t block_size, uint32_t Hkv, uint32_t D) const {
+    // [num_blocks, block_size, Hkv, D] 16-bit cache viewed as a 5-D tensor (64 | D/64 | Hkv | block_size | num_blocks):
+    // splitting D into 64-element halves keeps the innermost box at 128 bytes (the 128-byte swizzle's limit) while a
+    // token's D*2 bytes still arrive as one contiguous request.  Box = 16 tokens of one head of one page; a page index
+    // outside [0, num_blocks) is out of bounds and reads as zeros.
+    const cuuint64_t row = (cuuint64_t)D * 2;
+    cuuint64_t dims[5] = {64, D / 64, Hkv, block_size, num_blocks};
+    cuuint64_t strides[4] = {128, row, row * Hkv, row * Hkv * block_size};
+    cuuint32_t box[5] = {64, D / 64, 1, 16, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = drv_.cuTensorMapEncodeTiled(
+        m, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims,
+        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return check(r, "cuTensorMapEncodeTiled(paged cache)");
+}
+
+std::string Engine::paged_decode(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k_cache, CUdeviceptr v_cache,
+                                 CUdeviceptr block_tables, CUdeviceptr context_lens, CUdeviceptr out, uint32_t B,
+                                 uint32_t Hq, uint32_t Hkv, uint32_t D, uint32_t num_blocks, uint32_t block_size,
+                                 uint32_t max_blocks, uint32_t max_context, int32_t dtype, float scale, int32_t window) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    char buf[256];
+    if (dtype != kBF16 && dtype != kF16) return "paged decode needs a 16-bit cache (1=bf16, 2=f16)";
+    if (!B || !Hq || !Hkv || !num_blocks || !block_size || !max_blocks) return "empty tensor dimension";
+    if (Hq % Hkv != 0) {   // triton_flash_amd.py:696-697
+        snprintf(buf, sizeof(buf), "heads_q (%u) must be divisible by heads_kv (%u)", Hq, Hkv);
+        return buf;
+    }
+    if (Hq / Hkv > 16) return "paged decode supports at most 16 query heads per kv head";
+    if (D != 64 && D != 128) return "paged decode needs head_dim 64 or 128";
+    if (block_size % 16 != 0 || block_size > 256) return "paged decode needs block_size to be a multiple of 16, at most 256";
+    if (!q || !k_cache || !v_cache || !block_tables || !context_lens || !out) return "null device pointer";
+    if ((k_cache | v_cache) & 15) return "k_cache / v_cache must be 16-byte aligned";
+    if (q & 3) return "q must be 4-byte aligned";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    if (!(scale > 0.f)) scale = 1.0f / sqrtf((float)D);   // triton_flash_amd.py:699-700
+    if (window == 0) window = -1;
+
+    CUtensorMap tmK, tmV;
+    std::string e = make_tmap_paged(&tmK, dtype, k_cache, num_blocks, block_size, Hkv, D);
+    if (e.empty()) e = make_tmap_paged(&tmV, dtype, v_cache, num_blocks, block_size, Hkv, D);
+    if (!e.empty()) return e;
+
+    // Split count: fill the resident CTA slots (2 per SM) in one wave, at least 4 tiles (64 tokens) per split.
+    uint64_t span = max_context ? max_context : (uint64_t)max_blocks * block_size;
+    if (window > 0) span = std::min<uint64_t>(span, (uint64_t)window + 15);
+    const uint64_t tiles = (span + 15) / 16;
+    const uint64_t base = (uint64_t)B * Hkv, slots = 2ull * d.sm_count;
+    uint64_t nsplit = std::max<uint64_t>(1, slots / base);
+    nsplit = std::min<uint64_t>(nsplit, std::max<uint64_t>(1, tiles / 4));
+    nsplit = std::min<uint64_t>(nsplit, 128);
+    if (base * nsplit > 0x7fffffffull) return "problem too large (paged decode grid exceeds 2^31 CTAs)";
+
+    aule_kp::PagedParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = (const void*)q; p.out = (void*)out;
+    p.block_tables = (const int32_t*)block_tables; p.context_lens = (const int32_t*)context_lens;
+    p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.block_size = block_size; p.max_blocks = max_blocks;
+    p.nsplit = (uint32_t)nsplit; p.scale_log2 = scale * 1.4426950408889634f; p.window = window;
+    CUdeviceptr ws = 0;
+    if (nsplit > 1) {
+        const size_t rows = (size_t)B * Hq * nsplit;
+        const size_t o_bytes = rows * D * sizeof(float);
+        if (!(e = check(drv_.cuMemAllocAsync(&ws, o_bytes + rows * 2 * sizeof(float), stream), "cuMemAllocAsync(split workspace)")).empty()) return e;
+        p.ws_o = (float*)ws;
+        p.ws_ml = (float*)(ws + o_bytes);
+    }
+    const bool d128 = D == 128;
+    char name[64];
+    {
+        void* params[] = {&tmK, &tmV, &p};
+        snprintf(name, sizeof(name), "aule_paged_sm100_%s_d%u", kDtypeSuffix[dtype], D);
+        e = launch(d, d.paged[dtype][d128 ? 1 : 0], name, (unsigned)(base * nsplit), 1, 1,
+                   (unsigned)aule_kp::PagedCfg<128>::THREADS,
+                   d128 ? aule_kp::PagedCfg<128>::SMEM_BYTES : aule_kp::PagedCfg<64>::SMEM_BYTES, stream, params);
+    }
+    if (e.empty() && nsplit > 1) {
+        void* params[] = {&p, &D};
+        snprintf(name, sizeof(name), "aule_paged_combine_%s", kDtypeSuffix[dtype]);
+        e = launch(d, d.paged_combine[dtype], name, B * Hq, 1, 1, D, 0, stream, params);
+    }
+    if (ws) drv_.cuMemFreeAsync(ws, stream);
+    return e;
 }
 
 std::string Engine::mem_alloc(int dev, size_t bytes, CUdeviceptr* out) {

@@ -48,6 +48,8 @@ struct Device {
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dq_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // dQ kernel [dtype][D==128]
     CUfunction rope[3] = {nullptr, nullptr, nullptr};
+    CUfunction paged[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};     // decode kernel [dtype][D==128]
+    CUfunction paged_combine[3] = {nullptr, nullptr, nullptr};
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;
@@ -94,6 +96,14 @@ public:
     std::string rope(int dev, CUstream stream, CUdeviceptr x, CUdeviceptr out, CUdeviceptr cos, CUdeviceptr sin,
                      uint64_t bh, uint32_t S, uint32_t D, int32_t dtype, float sign);
 
+    // Paged-KV decode (one query token per sequence; python/aule/triton_flash_amd.py:662-740): q/out [B,Hq,D],
+    // k_cache/v_cache [num_blocks, block_size, Hkv, D], block_tables [B, max_blocks] i32, context_lens [B] i32.
+    // max_context (an upper bound of context_lens, 0 = max_blocks * block_size) only sizes the split count.
+    std::string paged_decode(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k_cache, CUdeviceptr v_cache,
+                             CUdeviceptr block_tables, CUdeviceptr context_lens, CUdeviceptr out, uint32_t B,
+                             uint32_t Hq, uint32_t Hkv, uint32_t D, uint32_t num_blocks, uint32_t block_size,
+                             uint32_t max_blocks, uint32_t max_context, int32_t dtype, float scale, int32_t window);
+
     // Raw memory for the handle-table tensors (device 0).
     std::string mem_alloc(int dev, size_t bytes, CUdeviceptr* out);
     void mem_free(int dev, CUdeviceptr p);
@@ -118,6 +128,8 @@ private:
     std::string launch(Device& d, CUfunction fn, const char* name, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
                        unsigned smem, CUstream stream, void** params);
     std::string make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D) const;
+    std::string make_tmap_paged(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint32_t num_blocks, uint32_t block_size,
+                                uint32_t Hkv, uint32_t D) const;
 
     CudaDriver drv_;
     std::vector<Device> devices_;

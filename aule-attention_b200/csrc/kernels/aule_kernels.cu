@@ -4,3 +4,4 @@
 #include "attn_simt.cu"
 #include "attn_fwd_sm100.cu"
 #include "attn_bwd_sm100.cu"
+#include "attn_paged_sm100.cu"

@@ -103,4 +103,38 @@ struct BwdDqCfg {
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
 };
 
+
+// ---- paged-KV decode (attn_paged_sm100.cu) --------------------------------------------
+// One query token per sequence against a block-table KV cache (vLLM layout):
+//   q [B,Hq,D] | k_cache, v_cache [num_blocks, block_size, Hkv, D] | block_tables [B, max_blocks] i32 | context_lens [B] i32
+struct PagedParams {
+    const void* q;               // [B,Hq,D]
+    void* out;                   // [B,Hq,D]
+    const int32_t* block_tables; // [B, max_blocks]
+    const int32_t* context_lens; // [B]
+    float* ws_o;                 // [B,Hq,nsplit,D] fp32 unnormalised partial outputs (nsplit > 1)
+    float* ws_ml;                // [B,Hq,nsplit,2] fp32 (running max in the log2 domain, partial row sum)
+    uint32_t B, Hq, Hkv;
+    uint32_t block_size;         // tokens per page, a multiple of 16
+    uint32_t max_blocks;         // row pitch of block_tables
+    uint32_t nsplit;             // CTAs sharing one (sequence, kv head)
+    float scale_log2;            // softmax scale * log2(e)
+    int32_t window;              // > 0: only the last `window` tokens of the context are visible; <= 0: all
+};
+template <int D>
+struct PagedCfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the paged decode path");
+    static constexpr int TOK = 16;                              // tokens per pipeline stage (one MMA k-step of P.V)
+    static constexpr int NS = (D == 128) ? 8 : 16;              // ring stages (K tile + V tile each)
+    static constexpr int CONSUMERS = 4;                         // MMA/softmax warps; warp 4 is the TMA producer
+    static constexpr int THREADS = (CONSUMERS + 1) * 32;
+    static constexpr uint32_t TILE_BYTES = TOK * D * 2;         // one K or V tile: [16 tokens][D/64 halves][128 B], 128B swizzle
+    static constexpr uint32_t STAGE_BYTES = 2 * TILE_BYTES;
+    static constexpr uint32_t OFF_RING = 0;
+    static constexpr uint32_t OFF_RED_O = NS * STAGE_BYTES;     // float [CONSUMERS][16 heads][D]
+    static constexpr uint32_t OFF_RED_ML = OFF_RED_O + CONSUMERS * 16 * D * 4;   // float [CONSUMERS][16][2]
+    static constexpr uint32_t OFF_BAR = OFF_RED_ML + CONSUMERS * 16 * 2 * 4;     // full[NS], empty[NS]
+    static constexpr uint32_t SMEM_BYTES = OFF_BAR + 2 * NS * 8 + 1024;          // + slack to align the ring to 1024 B
+};
+
 }  // namespace aule_kp

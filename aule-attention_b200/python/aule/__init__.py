@@ -138,6 +138,21 @@ def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size
     return _impl(q, k, v, cos, sin, causal=causal, scale=scale, window_size=window_size)
 
 
+def flash_attention_paged(q, k_cache, v_cache, block_tables, context_lens, scale=None, window_size=-1,
+                          max_context_len=None):
+    """PagedAttention decode (one query token per sequence, vLLM-style block tables) -- reference:
+    flash_attention_paged_amd, triton_flash_amd.py:662-740 (exported at __init__.py:59,575)."""
+    from .cuda_flash import flash_attention_paged as _impl
+    if not _cuda_available:
+        raise RuntimeError("aule (B200 build): CUDA sm_100 backend not available and there is no CPU fallback: "
+                           + _backend_errors.get('cuda', 'unknown error'))
+    return _impl(q, k_cache, v_cache, block_tables, context_lens, scale=scale, window_size=window_size,
+                 max_context_len=max_context_len)
+
+
+flash_attention_paged_amd = flash_attention_paged      # the name the reference exports (__init__.py:575)
+
+
 def precompute_rope_frequencies(seq_len, head_dim, base=10000.0, device="cuda", dtype=None):
     from .cuda_flash import precompute_rope_frequencies as _impl
     import torch
@@ -242,6 +257,7 @@ def print_backend_info():
 __all__ = [
     "flash_attention", "attention", "scaled_dot_product_attention",
     "flash_attention_rope", "precompute_rope_frequencies", "apply_rope_separate",
+    "flash_attention_paged", "flash_attention_paged_amd",
     "install", "uninstall",
     "get_available_backends", "get_backend_errors", "get_backend_info", "print_backend_info",
     "Aule", "GpuTensor", "AuleError",

@@ -189,3 +189,43 @@ def apply_rope_separate(q, k, cos, sin):
     cos_full = torch.cat([cos, cos], dim=-1)
     sin_full = torch.cat([sin, sin], dim=-1)
     return q * cos_full + rotate_half(q) * sin_full, k * cos_full + rotate_half(k) * sin_full
+
+
+def flash_attention_paged(q, k_cache, v_cache, block_tables, context_lens, scale=None, window_size=-1,
+                          max_context_len=None):
+    """Paged-KV decode: one query token per sequence against a vLLM-style block-table cache.
+
+    Mirror of triton_flash_amd.py:662-740 (`flash_attention_paged_amd`), same arguments:
+      q [batch, heads_q, head_dim] (or [batch, heads_q, 1, head_dim], :689-691)
+      k_cache, v_cache [num_blocks, block_size, num_kv_heads, head_dim]
+      block_tables [batch, max_blocks_per_seq] int32, context_lens [batch] int32
+    Returns [batch, heads_q, head_dim].  `max_context_len` (extra, optional): a host-side upper bound of
+    context_lens; the reference reads `context_lens.max().item()` back from the device on every call (:711) --
+    here nothing is read back, the bound only sizes the split-KV grid (default: max_blocks_per_seq * block_size).
+    """
+    lib = ffi.ensure_init()
+    if q.dim() == 4:
+        assert q.shape[2] == 1, "PagedAttention only supports single query token"
+        q = q.squeeze(2)
+    batch, heads_q, head_dim = q.shape
+    num_blocks_total, block_size, heads_kv, _ = k_cache.shape
+    assert heads_q % heads_kv == 0, f"heads_q ({heads_q}) must be divisible by heads_kv ({heads_kv})"   # :696-697
+    if k_cache.dtype not in (torch.bfloat16, torch.float16):
+        raise ffi.AuleError("PagedAttention failed: the KV cache must be bfloat16 or float16")
+    cdt = k_cache.dtype
+    if scale is None:
+        scale = 1.0 / math.sqrt(head_dim)                                # :699-700
+    orig_dtype = q.dtype
+    q = q.to(cdt).contiguous()                                           # :702-706
+    k_cache, v_cache = k_cache.contiguous(), v_cache.to(cdt).contiguous()
+    block_tables = block_tables.contiguous().to(torch.int32)
+    context_lens = context_lens.contiguous().to(torch.int32)
+    out = torch.empty(batch, heads_q, head_dim, device=q.device, dtype=cdt)   # :708
+    dev = q.device.index if q.device.index is not None else torch.cuda.current_device()
+    rc = lib.aule_attention_paged_decode_dptr(
+        q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), block_tables.data_ptr(), context_lens.data_ptr(),
+        out.data_ptr(), batch, heads_q, heads_kv, head_dim, num_blocks_total, block_size, block_tables.shape[1],
+        int(max_context_len or 0), _TORCH_TO_AULE[cdt], float(scale), int(window_size), dev,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc, "PagedAttention failed")
+    return out.to(orig_dtype)

@@ -71,6 +71,7 @@ def _proto(lib):
         "aule_attention_backward_dptr": ([u64] * 9 + [u32] * 6 + [i32, c.c_float, i32, i32, u64], i32),
         "aule_attention_forward_host": ([vp, vp, vp, vp, fp] + [u32] * 6 + [i32, c.c_float, i32, i32, i32], i32),
         "aule_rope_dptr": ([u64] * 4 + [u32] * 4 + [i32, i32, i32, u64], i32),
+        "aule_attention_paged_decode_dptr": ([u64] * 6 + [u32] * 8 + [i32, c.c_float, i32, i32, u64], i32),
         "aule_device_count": ([], i32), "aule_get_sm_count": ([i32], i32), "aule_synchronize": ([i32], i32),
         "aule_launch_count": ([], u64), "aule_last_kernel": ([], c.c_char_p), "aule_version": ([], c.c_char_p),
         "aule_set_kernel_path": ([i32], i32), "aule_set_trace_buffer": ([u64], i32), "aule_smoke_multiply": ([fp, fp, u32], i32),

@@ -106,12 +106,16 @@ AULE_API int32_t aule_attention_forward_gpu(uint64_t q, uint64_t k, uint64_t v, 
                                             uint64_t rot_cos, uint64_t rot_sin, int32_t causal,
                                             int32_t window_size);
 
-/* Out-of-scope product features (SURVEY 2.1 rows 13,14). Exported because
- * vulkan.py:300-316 sets their prototypes unconditionally; they return -10
- * ("unsupported") and set the error string.  lib.zig:533-624 */
+/* lib.zig:533-566 (AttentionEngine.forwardPaged, attention_gpu.zig:484-653): same tensors and result as
+ * aule_attention_forward_gpu -- the reference copies K/V into a private 32-token block pool first, which is an
+ * internal storage detail; here they go straight to the fused kernel.  codes: -1 bad handle, -3 compute error.
+ * (The serving-side paged KV cache with caller-owned block tables is aule_attention_paged_decode_dptr below.) */
 AULE_API int32_t aule_attention_forward_paged(uint64_t q, uint64_t k, uint64_t v, uint64_t output,
                                               uint64_t rot_cos, uint64_t rot_sin, int32_t causal,
                                               int32_t window_size);
+/* Out-of-scope product features (SURVEY 2.1 rows 13,14). Exported because
+ * vulkan.py:300-316 sets their prototypes unconditionally; they return -10
+ * ("unsupported") and set the error string.  lib.zig:568-624 */
 AULE_API int32_t aule_spatial_sort(uint64_t keys, uint64_t values, uint64_t indices,
                                    uint32_t sort_dim);
 AULE_API int32_t aule_attention_forward_gravity(uint64_t q, uint64_t k, uint64_t v, uint64_t output,
@@ -171,6 +175,26 @@ AULE_API int32_t aule_attention_forward_host(const void* q, const void* k, const
 AULE_API int32_t aule_rope_dptr(uint64_t x, uint64_t out, uint64_t cos, uint64_t sin, uint32_t B, uint32_t H,
                                 uint32_t S, uint32_t D, int32_t dtype, int32_t inverse, int32_t device,
                                 uint64_t cu_stream);
+
+/* Paged-KV decode on raw device pointers: one query token per sequence against a block-table
+ * KV cache in the vLLM layout.  Replaces flash_attention_paged_amd / _paged_attention_fwd_amd
+ * (python/aule/triton_flash_amd.py:662-740 / :544-660), same argument meaning:
+ *   q, out        [B, Hq, D]                              `dtype` (bf16 | f16)
+ *   k_cache/v_cache [num_blocks, block_size, Hkv, D]      `dtype`, contiguous, 16-byte aligned
+ *   block_tables  [B, max_blocks_per_seq] int32           page of tokens [i*block_size, (i+1)*block_size)
+ *   context_lens  [B] int32                               tokens of the sequence that are live (<= max_blocks*block_size)
+ *   scale <= 0 => 1/sqrt(D) (:699-700);  window > 0 keeps keys with (context_len-1-pos) < window (:618-621), -1 = all
+ *   kv head of q head h = h / (Hq/Hkv) (:573-575), Hq/Hkv <= 16;  D in {64,128};  block_size % 16 == 0, <= 256
+ *   max_context_len: an upper bound of context_lens known on the host (the reference reads it back with .item(),
+ *   :711); only sizes the split-KV grid, 0 = max_blocks_per_seq*block_size.  A sequence with context_len 0 gets zeros.
+ * Asynchronous on `cu_stream`; HBM-bound (reads each live K/V byte once per kv head).  -4 + error string on failure. */
+AULE_API int32_t aule_attention_paged_decode_dptr(uint64_t q, uint64_t k_cache, uint64_t v_cache,
+                                                  uint64_t block_tables, uint64_t context_lens, uint64_t out,
+                                                  uint32_t B, uint32_t Hq, uint32_t Hkv, uint32_t D,
+                                                  uint32_t num_blocks, uint32_t block_size,
+                                                  uint32_t max_blocks_per_seq, uint32_t max_context_len,
+                                                  int32_t dtype, float scale, int32_t window, int32_t device,
+                                                  uint64_t cu_stream);
 
 /* Device bookkeeping. */
 AULE_API int32_t aule_device_count(void);               /* sm_100 devices usable, -1 not init */

@@ -184,6 +184,39 @@ def rope_ref(x, cos, sin):
 #    tests/test_attention.zig:60-77 : max_abs < atol OR max_rel < rtol,
 #    relative error with a denominator floor.
 # --------------------------------------------------------------------------
+def paged_decode_ref(q, k_cache, v_cache, block_tables, context_lens, scale=None, window=-1, acc=np.float64):
+    """Paged-KV decode, restating the reference's decode kernel python/aule/triton_flash_amd.py:544-660
+    (argument meaning of the wrapper :662-740) as a gather + dense softmax:
+      q [B,Hq,D]; k_cache/v_cache [num_blocks, block_size, Hkv, D]; block_tables [B,max_blocks] int; context_lens [B] int
+      token j of sequence b lives in page block_tables[b, j // block_size] at slot j % block_size   (:597-605)
+      kv head of q head h is h // (Hq // Hkv)                                                      (:573-575)
+      valid tokens: j < context_len, and with window > 0 also (context_len - 1 - j) < window        (:613-621)
+    The reference's online-softmax loop over blocks is algebraically this softmax.  A sequence with
+    context_len == 0 returns zeros here (the reference computes 0/0)."""
+    q = np.asarray(q)
+    B, Hq, D = q.shape
+    _, bs, Hkv, _ = k_cache.shape
+    g = Hq // Hkv
+    if scale is None:
+        scale = 1.0 / np.sqrt(D)
+    out = np.zeros((B, Hq, D), dtype=acc)
+    for b in range(B):
+        n = int(context_lens[b])
+        if n <= 0:
+            continue
+        pos = np.arange(n)
+        pages = np.asarray(block_tables[b])[pos // bs]
+        k = np.asarray(k_cache)[pages, pos % bs].astype(acc)          # [n, Hkv, D]
+        v = np.asarray(v_cache)[pages, pos % bs].astype(acc)
+        keep = np.ones(n, dtype=bool) if window <= 0 else (n - 1 - pos) < window
+        for h in range(Hq):
+            s = (k[:, h // g, :] @ q[b, h].astype(acc)) * scale
+            s = np.where(keep, s, -np.inf)
+            p = np.exp(s - s.max())
+            out[b, h] = (p / p.sum()) @ v[:, h // g, :]
+    return out
+
+
 def max_abs_diff(a, b):
     """src/attention_ref.zig:189-197"""
     return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))))

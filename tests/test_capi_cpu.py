@@ -79,7 +79,13 @@ def test_error_convention_without_init(lib):
     assert lib.aule_get_vendor() == -1
     assert lib.aule_tensor_max() == 1024                   # lib.zig:16
     lib.aule_attention_forward_paged.argtypes = [ctypes.c_uint64] * 6 + [ctypes.c_int32] * 2
-    assert lib.aule_attention_forward_paged(0, 0, 0, 0, 0, 0, 0, -1) == -10
+    assert lib.aule_attention_forward_paged(0, 0, 0, 0, 0, 0, 0, -1) == -1      # lib.zig:544 (no context)
+    lib.aule_spatial_sort.argtypes = [ctypes.c_uint64] * 3 + [ctypes.c_uint32]
+    assert lib.aule_spatial_sort(0, 0, 0, 0) == -10                              # out of scope: loud stub
+    u64, u32, i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32
+    lib.aule_attention_paged_decode_dptr.argtypes = [u64] * 6 + [u32] * 8 + [i32, ctypes.c_float, i32, i32, u64]
+    assert lib.aule_attention_paged_decode_dptr(0, 0, 0, 0, 0, 0, 1, 1, 1, 64, 1, 16, 1, 0, 1, 0.0, -1, 0, 0) == -1
+    assert b"not initialized" in lib.aule_get_error().lower()
 
 
 def test_python_validation_matches_reference_messages():

@@ -227,3 +227,61 @@ def test_rope_ref_matches_reference_formulation():
     # rotation is orthogonal: transpose (negated sin) inverts it
     back = orc.rope_ref(exp.numpy(), cos.numpy(), -sin.numpy())
     np.testing.assert_allclose(back, x.numpy(), rtol=1e-12, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pinning against the reference's own Triton kernels (run unmodified under TRITON_INTERPRET=1 in the build
+# container by tests/golden/gen_golden_triton.py): GQA/MQA, scale, LSE, cross attention, window, backward, paged.
+def _triton_golden():
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "reference_triton_path.json")) as f:
+        meta = json.load(f)
+    return np.load(os.path.join(here, "reference_triton_path.npz")), meta
+
+
+_TG, _TM = _triton_golden()
+
+
+@pytest.mark.parametrize("name", sorted(_TM["fwd"]))
+def test_oracle_matches_reference_triton_kernels(name):
+    m = _TM["fwd"][name]
+    q, k, v, out = (_TG[f"{name}.{x}"] for x in ("q", "k", "v", "out"))
+    # the generic Triton kernel keeps keys with i - j <= W (triton_flash.py:190-193); this build's ABI uses the
+    # shader / AMD-kernel convention i - j < W (attention_f32.comp:176-178), so Triton's W is W + 1 here
+    w = m["window"] + 1 if m["window"] > 0 else -1
+    exp, lse = orc.attention_ref(q, k, v, causal=m["causal"], scale=m["scale"], window=w)
+    np.testing.assert_allclose(out, exp, rtol=0, atol=5e-6)
+    assert abs(float(out.astype(np.float64).sum()) - m["out_sum"]) < 1e-3
+    if m["backward"]:
+        dq, dk, dv, _, _ = orc.attention_bwd_ref(q, k, v, _TG[name + ".do"], causal=m["causal"], scale=m["scale"])
+        np.testing.assert_allclose(_TG[name + ".lse"], lse, rtol=0, atol=5e-6)     # LSE = m + ln l, triton_flash.py:231-235
+        for got, e in ((_TG[name + ".dq"], dq), (_TG[name + ".dk"], dk), (_TG[name + ".dv"], dv)):
+            np.testing.assert_allclose(got, e, rtol=0, atol=2e-5)                   # fp32 atomics in the reference
+
+
+@pytest.mark.parametrize("name", sorted(_TM["paged"]))
+def test_paged_oracle_matches_reference_triton_kernel(name):
+    m = _TM["paged"][name]
+    a = {x: _TG[f"{name}.{x}"] for x in ("q", "k_cache", "v_cache", "block_tables", "context_lens", "out")}
+    exp = orc.paged_decode_ref(a["q"], a["k_cache"], a["v_cache"], a["block_tables"], a["context_lens"], window=m["window"])
+    np.testing.assert_allclose(a["out"], exp, rtol=0, atol=2e-6)
+
+
+def test_paged_oracle_equals_dense_attention_on_gathered_cache():
+    """Gathering the pages and running the dense oracle's last causal row gives the same answer (GQA, ragged)."""
+    rng = np.random.default_rng(3)
+    B, Hq, Hkv, D, bs, nb, mb = 2, 6, 2, 32, 16, 20, 5
+    q = rng.standard_normal((B, Hq, D)).astype(np.float32)
+    kc, vc = (rng.standard_normal((nb, bs, Hkv, D)).astype(np.float32) for _ in range(2))
+    bt = rng.permutation(nb)[:B * mb].reshape(B, mb).astype(np.int32)
+    lens = np.array([71, 5], dtype=np.int32)
+    got = orc.paged_decode_ref(q, kc, vc, bt, lens)
+    for b in range(B):
+        n = int(lens[b])
+        pos = np.arange(n)
+        k = kc[bt[b][pos // bs], pos % bs].transpose(1, 0, 2)[None]     # [1,Hkv,n,D]
+        v = vc[bt[b][pos // bs], pos % bs].transpose(1, 0, 2)[None]
+        exp, _ = orc.attention_ref(q[b][None, :, None, :], k, v, causal=False)
+        np.testing.assert_allclose(got[b], exp[0, :, 0, :], rtol=1e-12, atol=1e-12)
+    assert np.all(orc.paged_decode_ref(q, kc, vc, bt, np.array([0, 0])) == 0)
