@@ -2,6 +2,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -610,6 +611,10 @@ std::string Engine::paged_decode(int dev, CUstream stream, CUdeviceptr q, CUdevi
     uint64_t nsplit = std::max<uint64_t>(1, slots / base);
     nsplit = std::min<uint64_t>(nsplit, std::max<uint64_t>(1, tiles / 4));
     nsplit = std::min<uint64_t>(nsplit, 128);
+    if (const char* ov = getenv("AULE_PAGED_NSPLIT")) {   // tuning hook (tools/bench_paged.py sweeps it)
+        const long v = atol(ov);
+        if (v > 0) nsplit = std::min<uint64_t>((uint64_t)v, std::max<uint64_t>(1, tiles));
+    }
     if (base * nsplit > 0x7fffffffull) return "problem too large (paged decode grid exceeds 2^31 CTAs)";
 
     aule_kp::PagedParams p;

@@ -107,34 +107,43 @@ __device__ __forceinline__ void paged_body(const CUtensorMap* tmK, const CUtenso
     __syncthreads();
 
     if (warp == NW) {
-        // ------------------------------------------------------------------ producer warp
-        const int32_t* table = p.block_tables + (size_t)b * p.max_blocks;
-        const uint32_t tiles_per_page = p.block_size / TOK;
-        auto fetch = [&](uint32_t base) -> int32_t {            // page of tile (base + lane), -1 past the range
-            const uint32_t t = base + lane;
-            if (t >= t1) return -1;
-            const uint32_t pg = t / tiles_per_page;
-            return pg < p.max_blocks ? table[pg] : -1;
-        };
-        int32_t cur = fetch(t0);
-        for (uint32_t base = t0; base < t1; base += 32) {
-            const int32_t nxt = fetch(base + 32);               // in flight while this batch is issued
-            const uint32_t n = min(32u, t1 - base);
-            for (uint32_t k = 0; k < n; ++k) {
-                const int32_t page = __shfl_sync(0xffffffffu, cur, k);
-                const uint32_t i = base + k - t0, s = i % NS;
-                if (lane == 0) {
-                    if (i >= NS) mbar_wait(bar_empty + s * 8, ((i / NS) - 1) & 1);
-                    const uint32_t dst = ring + s * Cfg::STAGE_BYTES;
-                    const int32_t tok = (int32_t)(((base + k) % tiles_per_page) * TOK);
-                    mbar_expect_tx(bar_full + s * 8, Cfg::STAGE_BYTES);
-                    // an out-of-range page index is out of bounds for the tensor map and reads as zeros
-                    tma_load_5d(dst, tmK, bar_full + s * 8, 0, 0, (int32_t)hkv, tok, page);
-                    tma_load_5d(dst + Cfg::TILE_BYTES, tmV, bar_full + s * 8, 0, 0, (int32_t)hkv, tok, page);
+        // ------------------------------------------------------------------ producer: ONE thread
+        // (A warp-wide loop with shuffles measured producer-bound: ~20 % of all issue slots went to broadcasting
+        // coordinates into uniform registers and to a runtime modulo per tile.)  The thread keeps the next PF block
+        // table entries in registers, loaded one group ahead, and advances (page, tile-in-page) incrementally.
+        if (lane == 0 && ntiles > 0) {
+            constexpr int PF = 16;
+            const int32_t* table = p.block_tables + (size_t)b * p.max_blocks;
+            const uint32_t tiles_per_page = p.block_size / TOK;
+            uint32_t pg = t0 / tiles_per_page;                  // first page of the range
+            uint32_t sub = t0 - pg * tiles_per_page;            // first 16-token tile inside it
+            const uint32_t pg_end = (t1 + tiles_per_page - 1) / tiles_per_page;
+            int32_t cur[PF], nxt[PF];
+#pragma unroll
+            for (int j = 0; j < PF; ++j) cur[j] = (pg + j < pg_end && pg + j < p.max_blocks) ? table[pg + j] : -1;
+            uint32_t i = 0;                                     // tile counter of this CTA
+            while (i < ntiles) {
+#pragma unroll
+                for (int j = 0; j < PF; ++j)
+                    nxt[j] = (pg + PF + j < pg_end && pg + PF + j < p.max_blocks) ? table[pg + PF + j] : -1;
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int32_t page = cur[j];
+                    for (; sub < tiles_per_page && i < ntiles; ++sub, ++i) {
+                        const uint32_t s = i % NS;
+                        if (i >= NS) mbar_wait(bar_empty + s * 8, ((i / NS) - 1) & 1);
+                        const uint32_t dst = ring + s * Cfg::STAGE_BYTES;
+                        mbar_expect_tx(bar_full + s * 8, Cfg::STAGE_BYTES);
+                        // an out-of-range page index is out of bounds for the tensor map and reads as zeros
+                        tma_load_5d(dst, tmK, bar_full + s * 8, 0, 0, (int32_t)hkv, (int32_t)(sub * TOK), page);
+                        tma_load_5d(dst + Cfg::TILE_BYTES, tmV, bar_full + s * 8, 0, 0, (int32_t)hkv, (int32_t)(sub * TOK), page);
+                    }
+                    sub = 0;
                 }
-                __syncwarp();
+                pg += PF;
+#pragma unroll
+                for (int j = 0; j < PF; ++j) cur[j] = nxt[j];
             }
-            cur = nxt;
         }
     } else {
         // ------------------------------------------------------------------ consumer warps

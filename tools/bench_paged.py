@@ -45,13 +45,15 @@ def run(name, B, Hq, Hkv, D, bs, ctx, window=-1, ragged=False, dtype=torch.bfloa
         call()
     torch.cuda.synchronize()
     ts = []
+    inner = 10                                   # back-to-back launches per sample: host launch latency is hidden
     for _ in range(REPS):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call()
+        for _ in range(inner):
+            call()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / inner)
     t = statistics.median(ts)
     res = {"config": name, "shape": {"B": B, "Hq": Hq, "Hkv": Hkv, "D": D, "block_size": bs, "context": ctx, "window": window,
                                      "ragged": ragged}, "kv_cache_MiB": round(2 * kc.numel() * 2 / 2**20, 1),
@@ -62,6 +64,15 @@ def run(name, B, Hq, Hkv, D, bs, ctx, window=-1, ragged=False, dtype=torch.bfloa
 
 
 if __name__ == "__main__":
+    if os.environ.get("AULE_PAGED_SWEEP"):
+        for ns in (1, 2, 3, 4, 7, 15):
+            os.environ["AULE_PAGED_NSPLIT"] = str(ns)
+            run(f"nsplit={ns} B=32 ctx=8192", 32, 32, 8, 128, 16, 8192)
+            run(f"nsplit={ns} ragged B=64 ctx<=8192", 64, 32, 8, 128, 16, 8192, ragged=True)
+        sys.exit(0)
+    if os.environ.get("AULE_PAGED_ONE"):
+        run("llama3-8b decode B=32 ctx=8192", 32, 32, 8, 128, 16, 8192)
+        sys.exit(0)
     run("llama3-8b decode B=32 ctx=8192", 32, 32, 8, 128, 16, 8192)
     run("llama3-8b decode B=8 ctx=32768", 8, 32, 8, 128, 16, 32768)
     run("llama3-8b decode B=128 ctx=2048", 128, 32, 8, 128, 16, 2048)
