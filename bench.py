@@ -204,6 +204,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; stdout is ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
