@@ -354,6 +354,10 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
             bp.order = bwd_serial_;
+            // dK/dV CTA order: all units at once.  Launching the KV-block CTAs of a few (batch, kv-head) units together
+            // (Q/dO L2-resident, BwdParams::units_per_run = ceil(SMs / KV blocks)) measured SLOWER: 1.36 vs 1.21 ms on
+            // config C/2 (gpurun s21) -- the heavy CTAs of later runs start late and the tail grows.
+            bp.units_per_run = 0;
             bp.trace = (unsigned long long*)trace_;
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;

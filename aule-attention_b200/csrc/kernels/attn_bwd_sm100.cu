@@ -47,17 +47,30 @@ struct Tracer {
 };
 
 // P phase for 32 columns of one row: exp2(S*c - lse2), masked when the block touches the diagonal / the ragged ends.
-template <bool MASK>
+// EMU of every 4 element pairs take the FMA-pipe polynomial exp2 (sm100::ex2_emu2) instead of MUFU.EX2: with four
+// compute warps per scheduler the 32 MUFU per thread and step are 1024 issue cycles per scheduler, the same as the
+// tensor time of the phase they run under.
+template <bool MASK, int EMU = 0>
 __device__ __forceinline__ void p_from_s(const uint32_t (&s)[32], float* pv, float c2, float lse2, uint32_t col0, uint32_t row,
                                          uint32_t Sk, bool row_ok, bool diag) {
+    const float2 cc = make_float2(c2, c2), nl = make_float2(-lse2, -lse2);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        float v = ex2(fmaf(__uint_as_float(s[e]), c2, -lse2));
+    for (int e = 0; e < 32; e += 2) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), cc, nl);
+        float2 v;
+        if (((e >> 1) & 3) < EMU) {
+            v = ex2_emu2(x);
+        } else {
+            v.x = ex2(x.x);
+            v.y = ex2(x.y);
+        }
         if (MASK) {
             const uint32_t col = col0 + e;
-            v = (row_ok && col < Sk && !(diag && col > row)) ? v : 0.f;
+            v.x = (row_ok && col < Sk && !(diag && col > row)) ? v.x : 0.f;
+            v.y = (row_ok && col + 1 < Sk && !(diag && col + 1 > row)) ? v.y : 0.f;
         }
-        pv[e] = v;
+        pv[e] = v.x;
+        pv[e + 1] = v.y;
     }
 }
 
@@ -118,8 +131,16 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
 
     // ---- which KV block
     const uint32_t per = p.Hkv * p.B;
-    const uint32_t jb = blockIdx.x / per;                            // KV block (0 = heaviest under causal)
-    const uint32_t bhk = blockIdx.x - jb * per;                      // b * Hkv + hk
+    // CTA order: runs of `units_per_run` (batch, kv-head) units; inside a run KV block 0 (heaviest under causal) of
+    // every unit first.  All KV-block CTAs of a unit stream the same Q / dO tiles: keeping only a few units in
+    // flight keeps those tiles L2-resident (all units at once re-read them from HBM 3.5x, ncu) and cuts the TMA
+    // latency the single dO buffer exposes.
+    const uint32_t nkb_grid = gridDim.x / per;
+    const uint32_t upr = (p.units_per_run == 0 || p.units_per_run > per) ? per : p.units_per_run;
+    const uint32_t run = blockIdx.x / (upr * nkb_grid), lw = blockIdx.x - run * upr * nkb_grid;
+    const uint32_t uir = min(upr, per - run * upr);                  // units in this run (the last may be short)
+    const uint32_t jb = lw / uir;                                    // KV block
+    const uint32_t bhk = run * upr + (lw - jb * uir);                // b * Hkv + hk
     const uint32_t b = bhk / p.Hkv, hk = bhk - b * p.Hkv;
     const uint32_t group = p.Hq / p.Hkv;
     const uint32_t key0 = jb * 128;
@@ -289,7 +310,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 if (lane == 0) mbar_arrive(bar_sfree);               // the buffer may take dP(step)
                 tr.ev(22, step);
                 if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
-                else p_from_s<false>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
+                else p_from_s<false, 1>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);   // 1 pair in 4 on the FMA pipe: -3 % (A/B, s20)
             }
             tr.ev(28, step);
             if (step > 0) mbar_wait(bar_dv, (step - 1) & 1);         // dV(step-1) has read the P buffer
@@ -597,7 +618,7 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmK, const CUtens
                 if (lane == 0) mbar_arrive(bar_sfree);               // one arrival per warp: the buffer may take dP(j)
                 tr.ev(22, j);
                 if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
-                else p_from_s<false>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
+                else p_from_s<false, 1>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);   // 1 pair in 4 on the FMA pipe: -3 % (A/B, s20)
             }
             // ---- dS phase: dS = P o (dP - Delta) -> 16-bit, in place over the first 16 of this thread's 32 dP columns
             tr.ev(23, j);

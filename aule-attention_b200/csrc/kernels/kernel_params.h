@@ -64,6 +64,8 @@ struct BwdParams {
     const float* lse;         // [B,Hq,Sq] natural-log LSE of the forward
     const float* delta;       // [B,Hq,Sq] rowsum(O o dO)
     uint32_t B, Hq, Hkv, Sq, Sk;
+    uint32_t units_per_run;   // dK/dV kernel: (batch, kv-head) units whose KV-block CTAs are launched together, so that the
+                              // Q and dO tiles they all stream stay L2-resident (0 = all units at once)
     float scale, scale_log2;
     int32_t causal;
     int32_t order;            // reserved for A/B tuning of the MMA issue order (unused by the shipped kernels)
