@@ -113,6 +113,14 @@ std::string Engine::load_device(int ordinal) {
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)BwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d128)");
+        if (e.empty()) e = get(&d.bwd_dkvt_sm100[t][0], std::string("aule_bwd_dkvt_sm100_") + kDtypeSuffix[t] + "_d64");
+        if (e.empty()) e = get(&d.bwd_dkvt_sm100[t][1], std::string("aule_bwd_dkvt_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_dkvt_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::BwdTCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dkvt d64)");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_dkvt_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::BwdTCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dkvt d128)");
         if (e.empty()) e = get(&d.bwd_dq_sm100[t][0], std::string("aule_bwd_dq_sm100_") + kDtypeSuffix[t] + "_d64");
         if (e.empty()) e = get(&d.bwd_dq_sm100[t][1], std::string("aule_bwd_dq_sm100_") + kDtypeSuffix[t] + "_d128");
         if (e.empty())
@@ -364,9 +372,16 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
             if (e.empty() && bwd_order_ != 2) {                 // (timing hook: 2 = dQ kernel only)
                 void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
-                snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
-                e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, (unsigned)BwdCfg<128>::THREADS,
-                           d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
+                if (bwd_serial_ & 2) {      // A/B hook (path bit 13): the v3 dK/dV kernel (P, dS staged through shared memory)
+                    snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+                    e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, (unsigned)BwdCfg<128>::THREADS,
+                               d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
+                } else {                    // v4: transposed score tiles, P^T / dS^T stay in TMEM
+                    snprintf(name, sizeof(name), "aule_bwd_dkvt_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+                    e = launch(d, d.bwd_dkvt_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1,
+                               (unsigned)aule_kp::BwdTCfg<128>::THREADS,
+                               d128 ? aule_kp::BwdTCfg<128>::SMEM_BYTES : aule_kp::BwdTCfg<64>::SMEM_BYTES, stream, params);
+                }
             }
             if (e.empty() && bwd_order_ != 1) {                 // (timing hook: 1 = dK/dV kernel only)
                 void* params[] = {&tmK, &tmV, &bp};

@@ -45,6 +45,7 @@ struct Device {
     CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     CUfunction fwd_sm100_var[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // bf16 tuning variants [D==128][v]
     CUfunction bwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
+    CUfunction bwd_dkvt_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // transposed dK/dV kernel (v4)
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dq_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // dQ kernel [dtype][D==128]
     CUfunction rope[3] = {nullptr, nullptr, nullptr};

@@ -99,24 +99,30 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
     // barriers
     const uint32_t bar_kv = sb + C::OFF_BAR;        // K_j, V_j landed (once)
     const uint32_t bar_q0 = bar_kv + 8;             // Q buffer 0 / 1 landed (+8)
-    const uint32_t bar_do = bar_kv + 24;            // dO landed
+    const uint32_t bar_do0 = bar_kv + 24;           // dO buffer 0 landed (buffer 1: bar_do1)
     const uint32_t bar_s0 = bar_kv + 32;            // S(i) complete in buffer i&1 (commit) (+8 for odd i)
     const uint32_t bar_dp0 = bar_kv + 48;           // dP(i) complete in buffer i&1 (commit) (+8 for odd i)
     const uint32_t bar_p = bar_kv + 64;             // compute -> issuer: P(i) in SMEM (one arrival per compute warp)
     const uint32_t bar_ds = bar_kv + 72;            // compute -> issuer: dS(i) in SMEM, buffer i&1 consumed (16 arrivals)
-    const uint32_t bar_dv = bar_kv + 80;            // dV(i) complete (commit): P buffer and dO buffer free
+    const uint32_t bar_dv0 = bar_kv + 80;           // dV(i) complete (commit), even i: P buffer and dO buffer 0 free (odd i: bar_dv1)
     const uint32_t bar_dk = bar_kv + 88;            // dK(i) complete (commit): dS buffer and Q buffer i&1 free
     const uint32_t bar_sfree = bar_kv + 96;         // compute -> issuer: S(i) copied to registers, its buffer may take dP(i) (16 arrivals)
+    const uint32_t bar_do1 = bar_kv + 104, bar_dv1 = bar_kv + 112;
+    // dV(i) commits to bar_dv[i&1] so that "dV(i-2) complete" (dO buffer i&1 reusable) can never be confused with
+    // dV(i-1): each of the two barriers completes once per two steps and its next completion needs the very load
+    // that is waiting on it.
+    auto bar_do = [&](uint32_t i) { return (i & 1) ? bar_do1 : bar_do0; };
+    auto bar_dv = [&](uint32_t i) { return (i & 1) ? bar_dv1 : bar_dv0; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
-    const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO = sb + C::OFF_DO,
+    const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO,
                    sP = sb + C::OFF_P, sdS = sb + C::OFF_DS;
 
     if (threadIdx.x == 0) {
         if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
-        mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1); mbar_init(bar_do, 1);
+        mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1); mbar_init(bar_do0, 1); mbar_init(bar_do1, 1);
         mbar_init(bar_s0, 1); mbar_init(bar_s0 + 8, 1); mbar_init(bar_dp0, 1); mbar_init(bar_dp0 + 8, 1);
         mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_sfree, 16);    // one arrival per compute warp
-        mbar_init(bar_dv, 1); mbar_init(bar_dk, 1);
+        mbar_init(bar_dv0, 1); mbar_init(bar_dv1, 1); mbar_init(bar_dk, 1);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
@@ -170,12 +176,18 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
                 for (int c = 0; c < C::CHUNKS; ++c) tma_load_3d(dst + c * C::CHUNK_BYTES, tmQ, bar, c * 64, row, bh);
+                if (step + 1 < nsteps) {                                     // the next Q tile is on the critical path
+                    coords(step + 1, row, bh);                               // (dK -> Q load -> S -> P): warm it in L2
+#pragma unroll
+                    for (int c = 0; c < C::CHUNKS; ++c) tma_prefetch_3d(tmQ, c * 64, row, bh);
+                }
             };
             auto load_do = [&](uint32_t step) {
                 int32_t row, bh; coords(step, row, bh);
-                mbar_expect_tx(bar_do, C::TILE_BYTES);
+                const uint32_t bar = bar_do(step), dst = sdO0 + (step & 1) * C::TILE_BYTES;
+                mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
-                for (int c = 0; c < C::CHUNKS; ++c) tma_load_3d(sdO + c * C::CHUNK_BYTES, tmdO, bar_do, c * 64, row, bh);
+                for (int c = 0; c < C::CHUNKS; ++c) tma_load_3d(dst + c * C::CHUNK_BYTES, tmdO, bar, c * 64, row, bh);
             };
             auto issue_s = [&](uint32_t step) {                              // S = Q K^T
                 const uint32_t sQ = sQ0 + (step & 1) * C::TILE_BYTES;
@@ -202,11 +214,11 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
             }
             Tracer tr(p.trace, 0, true);
             // ---- loads, issued from the wait loops as soon as their buffer is released:
-            //   Q(s)  -> buffer s&1 once dK(s-2) has read it;   dO(s) -> the single dO buffer once dV(s-1) has read it.
+            //   Q(s)  -> buffer s&1 once dK(s-2) has read it;   dO(s) -> buffer s&1 once dV(s-2) has read it.
             uint32_t ql = 0, dl = 0;
             auto pump = [&]() {
                 if (ql < nsteps && (ql < 2 || mbar_try_wait<0>(bar_dk, (ql - 2) & 1))) { load_q(ql); ++ql; }
-                if (dl < nsteps && (dl < 1 || mbar_try_wait<0>(bar_dv, (dl - 1) & 1))) { load_do(dl); ++dl; }
+                if (dl < nsteps && (dl < 2 || mbar_try_wait<0>(bar_dv(dl), ((dl - 2) >> 1) & 1))) { load_do(dl); ++dl; }
             };
             auto wait = [&](uint32_t bar, uint32_t parity) {
                 while (!mbar_try_wait<0>(bar, parity)) pump();
@@ -224,6 +236,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
             //   S(i+1)   [Q(i+1) landed]          -> buffer (i+1)&1 (its dP(i-1) was consumed with dS(i-1))
             //   dV(i)    [P(i) ready]             -> releases the dO buffer -> TMA dO(i+1)
             for (uint32_t step = 0; step < nsteps; ++step) {
+                const uint32_t sdO = sdO0 + (step & 1) * C::TILE_BYTES;
                 if (step > 0) {
                     wait(bar_ds, (step - 1) & 1);                            // dS(step-1) written, buffer (step-1)&1 consumed
                     tc_fence_after();
@@ -233,7 +246,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 tr.ev(10, step);
                 wait(bar_sfree, step & 1);                                   // S(step) is in registers
                 tr.ev(11, step);
-                wait(bar_do, step & 1);
+                wait(bar_do(step), (step >> 1) & 1);
                 tr.ev(12, step);
                 tc_fence_after();
 #pragma unroll
@@ -242,21 +255,27 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                     mma_ss(tmem + 128 * (step & 1), mk(HI_K_HI, (HI_K_LO | (sdO >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), ID_KK, kk > 0);
                 }
                 mma_commit(bar_dp0 + 8 * (step & 1));
+                auto issue_dv = [&]() {
+                    tr.ev(17, step);
+                    wait(bar_p, step & 1);                                   // P(step) written
+                    tr.ev(18, step);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)                           // dV += P^T dO   (K = 128 query rows)
+                        mma_ss(tmem + COL_DV, mk(HI_MN_HI, (HI_MN_LO | (sP >> 4)) + kk * 128), mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128),
+                               ID_MNMN, (step > 0 || kk > 0) ? 1u : 0u);
+                    mma_commit(bar_dv(step));
+                };
+                // With the shared P/dS buffer dV(step) gates dS(step) (and through it the next step): it goes first and
+                // S(step+1), which may still be waiting for its Q tile, after it.
+                if (C::SHARE_PDS) issue_dv();
                 if (step + 1 < nsteps) {
                     wait(bar_q0 + 8 * ((step + 1) & 1), ((step + 1) >> 1) & 1);   // (Q(step+1) is requested by pump once dK(step-1) is done)
                     tc_fence_after();
                     tr.ev(14, step);
                     issue_s(step + 1);
                 }
-                tr.ev(17, step);
-                wait(bar_p, step & 1);                                       // P(step) written
-                tr.ev(18, step);
-                tc_fence_after();
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)                               // dV += P^T dO   (K = 128 query rows)
-                    mma_ss(tmem + COL_DV, mk(HI_MN_HI, (HI_MN_LO | (sP >> 4)) + kk * 128), mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128),
-                           ID_MNMN, (step > 0 || kk > 0) ? 1u : 0u);
-                mma_commit(bar_dv);
+                if (!C::SHARE_PDS) issue_dv();
             }
             if (nsteps > 0) {
                 wait(bar_ds, (nsteps - 1) & 1);
@@ -313,7 +332,10 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 else p_from_s<false, 1>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);   // 1 pair in 4 on the FMA pipe: -3 % (A/B, s20)
             }
             tr.ev(28, step);
-            if (step > 0) mbar_wait(bar_dv, (step - 1) & 1);         // dV(step-1) has read the P buffer
+            if (step > 0) {
+                if (C::SHARE_PDS) mbar_wait(bar_dk, (step - 1) & 1);  // dK(step-1) has read dS(step-1) out of the shared buffer
+                else mbar_wait(bar_dv(step - 1), ((step - 1) >> 1) & 1);   // dV(step-1) has read the P buffer
+            }
             store_row32<BF16>(sP + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();                                // generic-proxy writes -> visible to the MMA (async proxy)
             tc_fence_before();
@@ -333,7 +355,8 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
                 for (int e = 0; e < 32; ++e) pv[e] *= (__uint_as_float(dp[e]) - delta);
             }
             tr.ev(25, step);
-            if (step > 0) mbar_wait(bar_dk, (step - 1) & 1);         // dK(step-1) has read the dS buffer
+            if (C::SHARE_PDS) mbar_wait(bar_dv(step), (step >> 1) & 1);   // dV(step) has read P(step) out of the shared buffer
+            else if (step > 0) mbar_wait(bar_dk, (step - 1) & 1);    // dK(step-1) has read the dS buffer
             tr.ev(26, step);
             store_row32<BF16>(sdS + (qt >> 1) * C::CHUNK_BYTES, r, qt & 1, pv);
             fence_proxy_async_smem();
@@ -344,7 +367,9 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
         }
     }
 
-    // ---- epilogue: dV, dK (x scale) -> 16-bit -> swizzled SMEM (P / dS buffers) -> TMA store
+    // ---- epilogue: dV, dK (x scale) -> 16-bit -> swizzled SMEM (P buffer; dS buffer, or Q buffer 0 when P and dS
+    //      share theirs) -> TMA store
+    const uint32_t sKst = C::SHARE_PDS ? sQ0 : sdS;
     __syncthreads();                                                 // every MMA is complete (the issuer waited on the last commit)
     tc_fence_after();
     if (warp < 16) {
@@ -353,7 +378,7 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
         {
             const int which = warp >> 3;                             // warps 0-7: dV, warps 8-15: dK
             const uint32_t col = (which ? COL_DK : COL_DV) + (D / 2) * h;
-            const uint32_t sbuf = which ? sdS : sP;
+            const uint32_t sbuf = which ? sKst : sP;
             const float mul = which ? p.scale : 1.f;
 #pragma unroll 1
             for (int c = 0; c < D / 64; ++c) {
@@ -386,7 +411,329 @@ __device__ __forceinline__ void bwd_dkv_body(const CUtensorMap* tmQ, const CUten
 #pragma unroll
         for (int c = 0; c < C::CHUNKS; ++c) {
             tma_store_3d(tmdV, sP + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
-            tma_store_3d(tmdK, sdS + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
+            tma_store_3d(tmdK, sKst + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
+        }
+        tma_store_commit();
+        tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc<512>(tmem);
+}
+
+// =====================================================================================================
+// dK/dV kernel, transposed form (v4).  Same CTA decomposition and the same dV / dK accumulators as bwd_dkv_body, but
+// the score tiles are computed TRANSPOSED -- S^T = K_j Q_i^T and dP^T = V_j dO_i^T, rows (TMEM lanes) = keys, columns =
+// queries -- so that P^T and dS^T, written back in place over their own fp32 columns, are directly the TMEM A operands
+// of  dV += P^T dO  and  dK += dS^T Q  (TS MMAs).  Nothing is staged through shared memory: the two 32 KB P / dS
+// buffers of bwd_dkv_body, their ~1200 cycles of st.shared + proxy fences per step and the single-buffered dO are
+// gone; the freed space holds a 3-stage Q ring and a 2-stage dO ring, which takes the TMA latency off the chain.
+//   TMEM: [0,128) S^T(i) -> P^T(i) | [128,256) dP^T(i) -> dS^T(i) | [256,384) dV | [384,512) dK
+//   tensor order per step i:   dV(i)  S^T(i+1)  dK(i)  dP^T(i+1)     (in-order execution closes the MMA->MMA hazards:
+//   S^T(i+1) overwrites P^T(i) after dV(i) has read it, dP^T(i+1) overwrites dS^T(i) after dK(i) has)
+// Row statistics are per COLUMN here (LSE_i, Delta_i of the 128 queries): 128 threads publish them one step ahead in
+// shared memory, every thread reads its 32 with broadcast LDS.128.
+template <int D, bool BF16>
+__device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
+                                               const CUtensorMap* tmdO, const CUtensorMap* tmdK, const CUtensorMap* tmdV,
+                                               const BwdParams& p) {
+    using C = aule_kp::BwdTCfg<D>;
+    constexpr int NQ = C::NQ, NDO = C::NDO;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_kv = sb + C::OFF_BAR;            // K_j, V_j landed (once)
+    const uint32_t bar_qfull0 = bar_kv + 8;             // Q stage s landed (+8s)
+    const uint32_t bar_qfree0 = bar_qfull0 + 8 * NQ;    // dK(i) complete (commit): Q stage i%NQ free (+8s)
+    const uint32_t bar_dofull0 = bar_qfree0 + 8 * NQ;   // dO stage s landed (+8s)
+    const uint32_t bar_dofree0 = bar_dofull0 + 8 * NDO; // dV(i) complete (commit): dO stage i%NDO free (+8s)
+    const uint32_t bar_s = bar_dofree0 + 8 * NDO;       // S^T(i) complete (commit)
+    const uint32_t bar_dp = bar_s + 8;                  // dP^T(i) complete (commit)
+    const uint32_t bar_p = bar_dp + 8;                  // compute -> issuer: P^T(i) in TMEM (16 arrivals)
+    const uint32_t bar_ds = bar_p + 8;                  // compute -> issuer: dS^T(i) in TMEM (16 arrivals)
+    const uint32_t bar_done = bar_ds + 8;               // every MMA complete (commit)
+    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 5) <= C::BAR_BYTES, "barrier area too small");
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
+    float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [2][lse2 x128 | delta x128]
+    const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO;
+
+    if (threadIdx.x == 0) {
+        if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
+        mbar_init(bar_kv, 1);
+        for (int i = 0; i < NQ; ++i) { mbar_init(bar_qfull0 + 8 * i, 1); mbar_init(bar_qfree0 + 8 * i, 1); }
+        for (int i = 0; i < NDO; ++i) { mbar_init(bar_dofull0 + 8 * i, 1); mbar_init(bar_dofree0 + 8 * i, 1); }
+        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_done, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
+    }
+    if (warp == 16) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 384;
+
+    // ---- which KV block
+    const uint32_t per = p.Hkv * p.B;
+    const uint32_t jb = blockIdx.x / per;                            // KV block (0 = heaviest under causal)
+    const uint32_t bhk = blockIdx.x - jb * per;                      // b * Hkv + hk
+    const uint32_t b = bhk / p.Hkv, hk = bhk - b * p.Hkv;
+    const uint32_t group = p.Hq / p.Hkv;
+    const uint32_t key0 = jb * 128;
+    const uint32_t nqb = (p.Sq + 127) / 128;
+    const uint32_t i_begin = p.causal ? jb : 0;                      // query blocks with rows >= key0 (top-left causal)
+    const uint32_t steps_per_head = (i_begin < nqb) ? (nqb - i_begin) : 0;
+    const uint32_t nsteps = steps_per_head * group;
+
+    if (warp == 16) {
+        // ===================================================== issuer
+        if (elect_one() && nsteps > 0) {
+            constexpr uint64_t HI_K = smem_desc_hi(16, 1024);                // K-major SW128
+            constexpr uint64_t HI_MN = smem_desc_hi(C::CHUNK_BYTES, 1024);   // MN-major SW128 (64-wide chunks 16 KB apart)
+            constexpr uint32_t HI_K_HI = uint32_t(HI_K >> 32), HI_K_LO = uint32_t(HI_K);
+            constexpr uint32_t HI_MN_HI = uint32_t(HI_MN >> 32), HI_MN_LO = uint32_t(HI_MN);
+            auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
+            constexpr uint32_t ID_KK = instr_desc_f16(BF16, 128, 128, false);    // A K-major, B K-major, N = 128 queries
+            constexpr uint32_t ID_KMN = instr_desc_f16(BF16, 128, D, true);      // A in TMEM, B MN-major, N = D
+            // (q-head of the group, query block) of the next Q / dO load, advanced without divisions
+            uint32_t ql = 0, ql_st = 0, ql_use = 0, ql_g = 0, ql_i = i_begin;
+            uint32_t dl = 0, dl_st = 0, dl_use = 0, dl_g = 0, dl_i = i_begin;
+            auto pump = [&]() {
+                if (ql < nsteps && (ql_use == 0 || mbar_try_wait<0>(bar_qfree0 + 8 * ql_st, (ql_use - 1) & 1))) {
+                    const uint32_t bar = bar_qfull0 + 8 * ql_st, dst = sQ0 + ql_st * C::TILE_BYTES;
+                    mbar_expect_tx(bar, C::TILE_BYTES);
+#pragma unroll
+                    for (int c = 0; c < C::CHUNKS; ++c)
+                        tma_load_3d(dst + c * C::CHUNK_BYTES, tmQ, bar, c * 64, (int32_t)(ql_i * 128), (int32_t)(b * p.Hq + hk * group + ql_g));
+                    ++ql;
+                    if (++ql_i == nqb) { ql_i = i_begin; ++ql_g; }
+                    if (++ql_st == NQ) { ql_st = 0; ++ql_use; }
+                }
+                if (dl < nsteps && (dl_use == 0 || mbar_try_wait<0>(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
+                    const uint32_t bar = bar_dofull0 + 8 * dl_st, dst = sdO0 + dl_st * C::TILE_BYTES;
+                    mbar_expect_tx(bar, C::TILE_BYTES);
+#pragma unroll
+                    for (int c = 0; c < C::CHUNKS; ++c)
+                        tma_load_3d(dst + c * C::CHUNK_BYTES, tmdO, bar, c * 64, (int32_t)(dl_i * 128), (int32_t)(b * p.Hq + hk * group + dl_g));
+                    ++dl;
+                    if (++dl_i == nqb) { dl_i = i_begin; ++dl_g; }
+                    if (++dl_st == NDO) { dl_st = 0; ++dl_use; }
+                }
+            };
+            auto wait = [&](uint32_t bar, uint32_t parity) {                 // blocking wait that keeps the loads flowing
+                while (!mbar_try_wait<0>(bar, parity)) pump();
+            };
+            auto issue_s = [&](uint32_t qst) {                               // S^T = K_j Q^T  (A = K_j, B = Q as [n = query][k = d])
+                const uint32_t sQ = sQ0 + qst * C::TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
+                    mma_ss(tmem + COL_S, mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sQ >> 4)) + off), ID_KK, kk > 0);
+                }
+                mma_commit(bar_s);
+            };
+            auto issue_dp = [&](uint32_t dst_) {                             // dP^T = V_j dO^T
+                const uint32_t sdO = sdO0 + dst_ * C::TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
+                    mma_ss(tmem + COL_DP, mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sdO >> 4)) + off), ID_KK, kk > 0);
+                }
+                mma_commit(bar_dp);
+            };
+            mbar_expect_tx(bar_kv, 2 * C::TILE_BYTES);
+#pragma unroll
+            for (int c = 0; c < C::CHUNKS; ++c) {
+                tma_load_3d(sK + c * C::CHUNK_BYTES, tmK, bar_kv, c * 64, (int32_t)key0, (int32_t)bhk);
+                tma_load_3d(sV + c * C::CHUNK_BYTES, tmV, bar_kv, c * 64, (int32_t)key0, (int32_t)bhk);
+            }
+            for (int t = 0; t < NQ; ++t) pump();                             // fill both rings
+            wait(bar_kv, 0);
+            wait(bar_qfull0, 0);
+            tc_fence_after();
+            issue_s(0);
+            wait(bar_dofull0, 0);
+            tc_fence_after();
+            issue_dp(0);
+            uint32_t qs = 0, qp = 0, ds_ = 0, dp_ = 0;                        // Q / dO stage of step i and the parity of its fill
+            for (uint32_t step = 0; step < nsteps; ++step) {
+                const uint32_t qs_next = (qs == NQ - 1) ? 0 : qs + 1, qp_next = (qs == NQ - 1) ? (qp ^ 1) : qp;
+                const uint32_t ds_next = (ds_ == NDO - 1) ? 0 : ds_ + 1, dp_next = (ds_ == NDO - 1) ? (dp_ ^ 1) : dp_;
+                wait(bar_p, step & 1);                                       // P^T(step) in TMEM
+                tc_fence_after();
+                {
+                    const uint32_t sdO = sdO0 + ds_ * C::TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)                           // dV += P^T dO   (K = 128 queries, A = P^T in TMEM)
+                        mma_ts(tmem + COL_DV, tmem + COL_S + 32 * (kk >> 1) + 8 * (kk & 1),
+                               mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128), ID_KMN, (step > 0 || kk > 0) ? 1u : 0u);
+                    mma_commit(bar_dofree0 + 8 * ds_);
+                }
+                if (step + 1 < nsteps) {
+                    wait(bar_qfull0 + 8 * qs_next, qp_next);
+                    tc_fence_after();
+                    issue_s(qs_next);                                        // overwrites P^T(step): after dV(step) in the pipe
+                }
+                wait(bar_ds, step & 1);                                      // dS^T(step) in TMEM
+                tc_fence_after();
+                {
+                    const uint32_t sQ = sQ0 + qs * C::TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)                           // dK += dS^T Q   (A = dS^T in TMEM)
+                        mma_ts(tmem + COL_DK, tmem + COL_DP + 32 * (kk >> 1) + 8 * (kk & 1),
+                               mk(HI_MN_HI, (HI_MN_LO | (sQ >> 4)) + kk * 128), ID_KMN, (step > 0 || kk > 0) ? 1u : 0u);
+                    mma_commit(bar_qfree0 + 8 * qs);
+                }
+                if (step + 1 < nsteps) {
+                    wait(bar_dofull0 + 8 * ds_next, dp_next);
+                    tc_fence_after();
+                    issue_dp(ds_next);                                       // overwrites dS^T(step): after dK(step) in the pipe
+                }
+                qs = qs_next; qp = qp_next; ds_ = ds_next; dp_ = dp_next;
+            }
+            mma_commit(bar_done);
+            wait(bar_done, 0);
+        }
+    } else {
+        // ===================================================== compute warps: thread == (key row, query quarter)
+        const uint32_t qt = warp >> 2;                               // query quarter: columns [32qt, 32qt+32)
+        const uint32_t r = (warp & 3) * 32 + lane;                   // key row of the tile == TMEM lane
+        const uint32_t lane_addr = ((warp & 3) * 32) << 16;
+        const uint32_t key = key0 + r;
+        const bool key_ok = key < p.Sk;
+        const uint32_t tS = tmem + lane_addr + COL_S + 32 * qt, tDP = tmem + lane_addr + COL_DP + 32 * qt;
+        // statistics publisher (warps 0-3: thread t publishes query t of the step): values of the NEXT step are
+        // fetched one step ahead
+        const uint32_t t128 = threadIdx.x;                           // < 128 for the publishers
+        float lse_n = 0.f, delta_n = 0.f;
+        uint32_t g_n = 0, i_n = i_begin;
+        auto fetch_stats = [&]() {
+            const uint32_t row = i_n * 128 + t128;
+            const size_t off = ((size_t)b * p.Hq + hk * group + g_n) * p.Sq;
+            const bool ok = row < p.Sq;
+            lse_n = ok ? p.lse[off + row] * 1.4426950408889634f : 0.f;
+            delta_n = ok ? p.delta[off + row] : 0.f;
+            if (++i_n == nqb) { i_n = i_begin; ++g_n; }
+        };
+        if (warp < 4 && nsteps > 0) {
+            fetch_stats();
+            stat[t128] = lse_n; stat[128 + t128] = delta_n;          // step 0 -> buffer 0
+            if (nsteps > 1) fetch_stats();                           // step 1, published at the top of step 0
+        }
+        uint32_t i = i_begin;
+        for (uint32_t step = 0; step < nsteps; ++step) {
+            named_bar_sync(1, 512);                                  // everyone is done with buffer (step+1)&1; buffer step&1 is published
+            if (warp < 4 && step + 1 < nsteps) {
+                float* sn = stat + ((step + 1) & 1) * 256;
+                sn[t128] = lse_n; sn[128 + t128] = delta_n;
+                if (step + 2 < nsteps) fetch_stats();
+            }
+            const float* sc = stat + (step & 1) * 256 + 32 * qt;     // this quarter's 32 lse2, then (+128) its 32 deltas
+            const uint32_t q0 = i * 128 + 32 * qt;                   // first query of this thread's columns
+            const bool diag = p.causal && (i * 128 < key0 + 128);
+            const bool masked = diag || !key_ok || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
+            if (++i == nqb) i = i_begin;
+
+            // ---- P phase: P^T = exp2(S^T*scale_log2 - lse2[query]) -> 16-bit, in place over the first 16 columns
+            float pv[32];
+            mbar_wait(bar_s, step & 1);
+            tc_fence_after();
+            {
+                uint32_t s[32];
+                tmem_ld32(tS, s);
+                tmem_wait_ld();
+                const float2 cc = make_float2(p.scale_log2, p.scale_log2);
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(sc + 4 * e4);       // broadcast
+                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
+                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
+                    float2 v0, v1;
+                    if ((e4 & 1) == 0) { v0 = ex2_emu2(x0); } else { v0.x = ex2(x0.x); v0.y = ex2(x0.y); }   // 1 pair in 4 on the FMA pipe
+                    v1.x = ex2(x1.x); v1.y = ex2(x1.y);
+                    pv[4 * e4] = v0.x; pv[4 * e4 + 1] = v0.y; pv[4 * e4 + 2] = v1.x; pv[4 * e4 + 3] = v1.y;
+                }
+                if (masked) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const uint32_t q = q0 + e;
+                        pv[e] = (key_ok && q < p.Sq && !(diag && key > q)) ? pv[e] : 0.f;
+                    }
+                }
+            }
+            {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[e] = pack2<BF16>(pv[2 * e], pv[2 * e + 1]);
+                tmem_st16(tS, pk);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_p);
+            }
+            // ---- dS phase: dS^T = P^T o (dP^T - delta[query]) -> 16-bit, in place
+            mbar_wait(bar_dp, step & 1);
+            tc_fence_after();
+            {
+                uint32_t dp[32], pk[16];
+                tmem_ld32(tDP, dp);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(sc + 128 + 4 * e4);  // broadcast
+                    pk[2 * e4] = pack2<BF16>(pv[4 * e4] * (__uint_as_float(dp[4 * e4]) - d4.x), pv[4 * e4 + 1] * (__uint_as_float(dp[4 * e4 + 1]) - d4.y));
+                    pk[2 * e4 + 1] = pack2<BF16>(pv[4 * e4 + 2] * (__uint_as_float(dp[4 * e4 + 2]) - d4.z), pv[4 * e4 + 3] * (__uint_as_float(dp[4 * e4 + 3]) - d4.w));
+                }
+                tmem_st16(tDP, pk);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ds);
+            }
+        }
+    }
+
+    // ---- epilogue: dV, dK (x scale) -> 16-bit -> swizzled SMEM (Q stage 0 / dO stage 0, free now) -> TMA store
+    __syncthreads();                                                 // every MMA is complete (the issuer waited on bar_done)
+    tc_fence_after();
+    if (warp < 16) {
+        const uint32_t h = (warp >> 2) & 1, r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = ((warp & 3) * 32) << 16;
+        const int which = warp >> 3;                                 // warps 0-7: dV, warps 8-15: dK
+        const uint32_t col = (which ? COL_DK : COL_DV) + (D / 2) * h;
+        const uint32_t sbuf = which ? sdO0 : sQ0;
+        const float mul = which ? p.scale : 1.f;
+#pragma unroll 1
+        for (int c = 0; c < D / 64; ++c) {
+            uint32_t o[32];
+            if (nsteps > 0) {
+                tmem_ld32(tmem + lane_addr + col + c * 32, o);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[e] = 0u;               // no visible query touches this KV block
+            }
+            const uint32_t dcol = (D / 2) * h + c * 32;              // first output column of this chunk
+            const uint32_t chunk = dcol / 64, unit0 = (dcol % 64) / 8;
+            const uint32_t rowbase = sbuf + chunk * C::CHUNK_BYTES + r * 128;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t v0 = pack2<BF16>(__uint_as_float(o[8 * u + 0]) * mul, __uint_as_float(o[8 * u + 1]) * mul);
+                const uint32_t v1 = pack2<BF16>(__uint_as_float(o[8 * u + 2]) * mul, __uint_as_float(o[8 * u + 3]) * mul);
+                const uint32_t v2 = pack2<BF16>(__uint_as_float(o[8 * u + 4]) * mul, __uint_as_float(o[8 * u + 5]) * mul);
+                const uint32_t v3 = pack2<BF16>(__uint_as_float(o[8 * u + 6]) * mul, __uint_as_float(o[8 * u + 7]) * mul);
+                const uint32_t addr = rowbase + (((unit0 + u) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+            }
+        }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < C::CHUNKS; ++c) {
+            tma_store_3d(tmdV, sQ0 + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
+            tma_store_3d(tmdK, sdO0 + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
         }
         tma_store_commit();
         tma_store_wait_all<0>();
@@ -690,6 +1037,20 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmK, const CUtens
         bwd100::bwd_dq_body<DD, BF>(&tmK, &tmV, p);                                                       \
     }
 
+#define AULE_BWD100_T(NAME, DD, BF)                                                                      \
+    extern "C" __global__ void __launch_bounds__(544, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
+                                                              const __grid_constant__ CUtensorMap tmK,    \
+                                                              const __grid_constant__ CUtensorMap tmV,    \
+                                                              const __grid_constant__ CUtensorMap tmdO,   \
+                                                              const __grid_constant__ CUtensorMap tmdK,   \
+                                                              const __grid_constant__ CUtensorMap tmdV,   \
+                                                              const aule_kp::BwdParams p) {               \
+        bwd100::bwd_dkv_t_body<DD, BF>(&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, p);                         \
+    }
+AULE_BWD100_T(aule_bwd_dkvt_sm100_bf16_d128, 128, true)
+AULE_BWD100_T(aule_bwd_dkvt_sm100_bf16_d64, 64, true)
+AULE_BWD100_T(aule_bwd_dkvt_sm100_f16_d128, 128, false)
+AULE_BWD100_T(aule_bwd_dkvt_sm100_f16_d64, 64, false)
 AULE_BWD100(aule_bwd_sm100_bf16_d128, 128, true)
 AULE_BWD100(aule_bwd_sm100_bf16_d64, 64, true)
 AULE_BWD100(aule_bwd_sm100_f16_d128, 128, false)

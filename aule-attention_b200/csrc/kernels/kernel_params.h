@@ -80,12 +80,36 @@ struct BwdCfg {
     static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
     static constexpr uint32_t OFF_K = 0, OFF_V = TILE_BYTES;
     static constexpr uint32_t OFF_Q = 2 * TILE_BYTES;           // Q double-buffered
-    static constexpr uint32_t OFF_DO = 4 * TILE_BYTES;
-    static constexpr uint32_t OFF_P = 5 * TILE_BYTES;           // P  [128 q rows][128 keys] 16-bit
-    static constexpr uint32_t OFF_DS = OFF_P + 2 * CHUNK_BYTES; // dS same shape
+    static constexpr uint32_t OFF_DO = 4 * TILE_BYTES;          // dO double-buffered
+    static constexpr uint32_t OFF_P = 6 * TILE_BYTES;           // P  [128 q rows][128 keys] 16-bit
+    // D = 128: 6 operand tiles are 192 KB, so P(i) and dS(i) take turns in ONE 32 KB buffer (dS(i) is written after
+    // dV(i) has read P(i); P(i+1) after dK(i) has read dS(i)).  D = 64 has room for both.
+    static constexpr bool SHARE_PDS = (D == 128);
+    static constexpr uint32_t OFF_DS = SHARE_PDS ? OFF_P : OFF_P + 2 * CHUNK_BYTES;   // dS same shape
     static constexpr uint32_t OFF_BAR = OFF_DS + 2 * CHUNK_BYTES;
-    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 128;          // 13 mbarriers
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + 128;          // 15 mbarriers
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+};
+
+// dK/dV kernel, transposed form (S^T = K Q^T, dP^T = V dO^T; P^T and dS^T stay in TMEM as A operands):
+// K_j | V_j | Q ring (3) | dO ring (2) | row statistics (2 x [lse2 128 | delta 128]) | barriers.  No P / dS staging.
+template <int D>
+struct BwdTCfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
+    static constexpr int THREADS = 544;
+    static constexpr int NQ = 3, NDO = 2;
+    static constexpr int CHUNKS = D / 64;
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_K = 0, OFF_V = TILE_BYTES;
+    static constexpr uint32_t OFF_Q = 2 * TILE_BYTES;
+    static constexpr uint32_t OFF_DO = (2 + NQ) * TILE_BYTES;
+    static constexpr uint32_t OFF_STAT = (2 + NQ + NDO) * TILE_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 256 * 4;
+    static constexpr uint32_t BAR_BYTES = 160;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
 // dQ kernel (query block outer): K ring | V ring | barriers   (Q, dO, dS live in TMEM)

@@ -102,6 +102,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// global -> L2 only (no shared-memory destination): warms the tile a later tma_load_3d will fetch.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // shared -> global, 3-D tile (out-of-bounds rows are clipped by the hardware).
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_smem,
                                              int32_t c0, int32_t c1, int32_t c2) {
