@@ -35,8 +35,14 @@ using namespace sm100;
 using aule_kp::BwdParams;
 template <int D> using Cfg = aule_kp::BwdCfg<D>;
 
-// Bring-up tracer (aule_set_trace_buffer): CTA 0 only, one region of 4096 entries per traced thread.
+// Bring-up tracer (aule_set_trace_buffer): CTA 0 only, one region of 4096 entries per traced thread.  Compiled in only
+// with -DAULE_BWD_TRACE=1 (make EXTRA_NVFLAGS=-DAULE_BWD_TRACE=1; tools/bwd_trace.py): even disabled at run time its
+// checks cost ~16 instructions per thread and step in kernels whose compute warps are issue-bound.
+#ifndef AULE_BWD_TRACE
+#define AULE_BWD_TRACE 0
+#endif
 struct Tracer {
+#if AULE_BWD_TRACE
     unsigned long long* buf;
     uint32_t n;
     __device__ __forceinline__ Tracer(unsigned long long* base, uint32_t region, bool on)
@@ -44,6 +50,10 @@ struct Tracer {
     __device__ __forceinline__ void ev(uint32_t code, uint32_t step) {
         if (buf && n < 4096) buf[n++] = ((unsigned long long)((code << 8) | (step & 255u)) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
     }
+#else
+    __device__ __forceinline__ Tracer(unsigned long long*, uint32_t, bool) {}
+    __device__ __forceinline__ void ev(uint32_t, uint32_t) {}
+#endif
 };
 
 // P phase for 32 columns of one row: exp2(S*c - lse2), masked when the block touches the diagonal / the ragged ends.
@@ -452,9 +462,12 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
     const uint32_t bar_p = bar_dp + 8;                  // compute -> issuer: P^T(i) in TMEM (16 arrivals)
     const uint32_t bar_ds = bar_p + 8;                  // compute -> issuer: dS^T(i) in TMEM (16 arrivals)
     const uint32_t bar_done = bar_ds + 8;               // every MMA complete (commit)
-    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 5) <= C::BAR_BYTES, "barrier area too small");
+    const uint32_t bar_stat0 = bar_done + 8;            // publishers -> everyone: statistics of step s are in buffer s&1 (4 arrivals);
+                                                        // one barrier per buffer, so a waiter can never be lapped (the next
+                                                        // completion of ITS barrier needs its own dS^T arrival two steps on)
+    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 7) <= C::BAR_BYTES, "barrier area too small");
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
-    float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [2][lse2 x128 | delta x128]
+    float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [3][lse2 x128 | delta x128]
     const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO;
 
     if (threadIdx.x == 0) {
@@ -463,6 +476,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
         for (int i = 0; i < NQ; ++i) { mbar_init(bar_qfull0 + 8 * i, 1); mbar_init(bar_qfree0 + 8 * i, 1); }
         for (int i = 0; i < NDO; ++i) { mbar_init(bar_dofull0 + 8 * i, 1); mbar_init(bar_dofree0 + 8 * i, 1); }
         mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_done, 1);
+        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
@@ -555,11 +569,14 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             wait(bar_dofull0, 0);
             tc_fence_after();
             issue_dp(0);
+            Tracer tr(p.trace, 0, true);
             uint32_t qs = 0, qp = 0, ds_ = 0, dp_ = 0;                        // Q / dO stage of step i and the parity of its fill
             for (uint32_t step = 0; step < nsteps; ++step) {
                 const uint32_t qs_next = (qs == NQ - 1) ? 0 : qs + 1, qp_next = (qs == NQ - 1) ? (qp ^ 1) : qp;
                 const uint32_t ds_next = (ds_ == NDO - 1) ? 0 : ds_ + 1, dp_next = (ds_ == NDO - 1) ? (dp_ ^ 1) : dp_;
+                tr.ev(17, step);
                 wait(bar_p, step & 1);                                       // P^T(step) in TMEM
+                tr.ev(18, step);
                 tc_fence_after();
                 {
                     const uint32_t sdO = sdO0 + ds_ * C::TILE_BYTES;
@@ -571,10 +588,12 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 }
                 if (step + 1 < nsteps) {
                     wait(bar_qfull0 + 8 * qs_next, qp_next);
+                    tr.ev(14, step);
                     tc_fence_after();
                     issue_s(qs_next);                                        // overwrites P^T(step): after dV(step) in the pipe
                 }
                 wait(bar_ds, step & 1);                                      // dS^T(step) in TMEM
+                tr.ev(13, step);
                 tc_fence_after();
                 {
                     const uint32_t sQ = sQ0 + qs * C::TILE_BYTES;
@@ -586,6 +605,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 }
                 if (step + 1 < nsteps) {
                     wait(bar_dofull0 + 8 * ds_next, dp_next);
+                    tr.ev(12, step);
                     tc_fence_after();
                     issue_dp(ds_next);                                       // overwrites dS^T(step): after dK(step) in the pipe
                 }
@@ -602,8 +622,10 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
         const uint32_t key = key0 + r;
         const bool key_ok = key < p.Sk;
         const uint32_t tS = tmem + lane_addr + COL_S + 32 * qt, tDP = tmem + lane_addr + COL_DP + 32 * qt;
-        // statistics publisher (warps 0-3: thread t publishes query t of the step): values of the NEXT step are
-        // fetched one step ahead
+        // Statistics publishers (warps 0-3: thread t publishes query t): the values of step s+1 are written to buffer
+        // (s+1)&1 during the dS phase of step s -- once dP^T(s) is complete every warp has finished step s-1, the last
+        // reader of that buffer -- from registers fetched a step earlier (nothing here waits on a global load), and
+        // announced on bar_stat.
         const uint32_t t128 = threadIdx.x;                           // < 128 for the publishers
         float lse_n = 0.f, delta_n = 0.f;
         uint32_t g_n = 0, i_n = i_begin;
@@ -611,23 +633,25 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             const uint32_t row = i_n * 128 + t128;
             const size_t off = ((size_t)b * p.Hq + hk * group + g_n) * p.Sq;
             const bool ok = row < p.Sq;
-            lse_n = ok ? p.lse[off + row] * 1.4426950408889634f : 0.f;
+            lse_n = ok ? p.lse[off + row] : 0.f;
             delta_n = ok ? p.delta[off + row] : 0.f;
             if (++i_n == nqb) { i_n = i_begin; ++g_n; }
         };
+        auto publish = [&](uint32_t s_) {                            // statistics of step s_ -> buffer s_&1, one arrival per warp
+            float* sn = stat + (s_ & 1) * 256;
+            sn[t128] = lse_n * 1.4426950408889634f; sn[128 + t128] = delta_n;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_stat0 + 8 * (s_ & 1));
+        };
         if (warp < 4 && nsteps > 0) {
             fetch_stats();
-            stat[t128] = lse_n; stat[128 + t128] = delta_n;          // step 0 -> buffer 0
-            if (nsteps > 1) fetch_stats();                           // step 1, published at the top of step 0
+            publish(0);
+            if (nsteps > 1) fetch_stats();                           // step 1, published during step 0
         }
+        Tracer tr(p.trace, 1 + (qt & 1), (warp == 0 || warp == 4) && lane == 0);
         uint32_t i = i_begin;
         for (uint32_t step = 0; step < nsteps; ++step) {
-            named_bar_sync(1, 512);                                  // everyone is done with buffer (step+1)&1; buffer step&1 is published
-            if (warp < 4 && step + 1 < nsteps) {
-                float* sn = stat + ((step + 1) & 1) * 256;
-                sn[t128] = lse_n; sn[128 + t128] = delta_n;
-                if (step + 2 < nsteps) fetch_stats();
-            }
+            mbar_wait(bar_stat0 + 8 * (step & 1), (step >> 1) & 1);  // statistics of this step are visible
             const float* sc = stat + (step & 1) * 256 + 32 * qt;     // this quarter's 32 lse2, then (+128) its 32 deltas
             const uint32_t q0 = i * 128 + 32 * qt;                   // first query of this thread's columns
             const bool diag = p.causal && (i * 128 < key0 + 128);
@@ -636,12 +660,15 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
 
             // ---- P phase: P^T = exp2(S^T*scale_log2 - lse2[query]) -> 16-bit, in place over the first 16 columns
             float pv[32];
+            tr.ev(20, step);
             mbar_wait(bar_s, step & 1);
+            tr.ev(21, step);
             tc_fence_after();
             {
                 uint32_t s[32];
                 tmem_ld32(tS, s);
                 tmem_wait_ld();
+                tr.ev(22, step);
                 const float2 cc = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
@@ -649,7 +676,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
                     const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
                     float2 v0, v1;
-                    if ((e4 & 1) == 0) { v0 = ex2_emu2(x0); } else { v0.x = ex2(x0.x); v0.y = ex2(x0.y); }   // 1 pair in 4 on the FMA pipe
+                    if ((e4 & 1) == 0 || (p.order & 4)) { v0 = ex2_emu2(x0); } else { v0.x = ex2(x0.x); v0.y = ex2(x0.y); }   // 1 (A/B: 2) pair(s) in 4 on the FMA pipe
                     v1.x = ex2(x1.x); v1.y = ex2(x1.y);
                     pv[4 * e4] = v0.x; pv[4 * e4 + 1] = v0.y; pv[4 * e4 + 2] = v1.x; pv[4 * e4 + 3] = v1.y;
                 }
@@ -661,6 +688,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     }
                 }
             }
+            tr.ev(28, step);
             {
                 uint32_t pk[16];
 #pragma unroll
@@ -671,9 +699,15 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_p);
             }
+            tr.ev(23, step);
             // ---- dS phase: dS^T = P^T o (dP^T - delta[query]) -> 16-bit, in place
             mbar_wait(bar_dp, step & 1);
+            tr.ev(24, step);
             tc_fence_after();
+            if (warp < 4 && step + 1 < nsteps) {
+                publish(step + 1);
+                if (step + 2 < nsteps) fetch_stats();
+            }
             {
                 uint32_t dp[32], pk[16];
                 tmem_ld32(tDP, dp);
@@ -681,15 +715,21 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
                     const float4 d4 = *reinterpret_cast<const float4*>(sc + 128 + 4 * e4);  // broadcast
-                    pk[2 * e4] = pack2<BF16>(pv[4 * e4] * (__uint_as_float(dp[4 * e4]) - d4.x), pv[4 * e4 + 1] * (__uint_as_float(dp[4 * e4 + 1]) - d4.y));
-                    pk[2 * e4 + 1] = pack2<BF16>(pv[4 * e4 + 2] * (__uint_as_float(dp[4 * e4 + 2]) - d4.z), pv[4 * e4 + 3] * (__uint_as_float(dp[4 * e4 + 3]) - d4.w));
+                    const float2 a0 = __fmul2_rn(make_float2(pv[4 * e4], pv[4 * e4 + 1]),
+                                                 __fadd2_rn(make_float2(__uint_as_float(dp[4 * e4]), __uint_as_float(dp[4 * e4 + 1])), make_float2(-d4.x, -d4.y)));
+                    const float2 a1 = __fmul2_rn(make_float2(pv[4 * e4 + 2], pv[4 * e4 + 3]),
+                                                 __fadd2_rn(make_float2(__uint_as_float(dp[4 * e4 + 2]), __uint_as_float(dp[4 * e4 + 3])), make_float2(-d4.z, -d4.w)));
+                    pk[2 * e4] = pack2<BF16>(a0.x, a0.y);
+                    pk[2 * e4 + 1] = pack2<BF16>(a1.x, a1.y);
                 }
+                tr.ev(25, step);
                 tmem_st16(tDP, pk);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ds);
             }
+            tr.ev(27, step);
         }
     }
 
@@ -978,8 +1018,11 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmK, const CUtens
                 tmem_ld32(tbuf, dp);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    pk[e] = pack2<BF16>(pv[2 * e] * (__uint_as_float(dp[2 * e]) - delta), pv[2 * e + 1] * (__uint_as_float(dp[2 * e + 1]) - delta));
+                for (int e = 0; e < 16; ++e) {
+                    const float2 a = __fmul2_rn(make_float2(pv[2 * e], pv[2 * e + 1]),
+                                                __fadd2_rn(make_float2(__uint_as_float(dp[2 * e]), __uint_as_float(dp[2 * e + 1])), make_float2(-delta, -delta)));
+                    pk[e] = pack2<BF16>(a.x, a.y);
+                }
             }
             tr.ev(25, j);
             tmem_st16(tbuf, pk);

@@ -1,5 +1,7 @@
 """Per-step pipeline timeline of the backward kernels (bring-up tool): CTA 0 records clock64 at its pipeline events
 through aule_set_trace_buffer; this prints, per step, the event times relative to the step's first event.
+The tracer is compiled in only with  make -C aule-attention_b200 EXTRA_NVFLAGS=-DAULE_BWD_TRACE=1  (rebuild without it
+afterwards: the checks cost instructions in issue-bound kernels).
 usage: python tools/bwd_trace.py [dq|dkv] [first_step] [last_step]"""
 import os
 import sys
@@ -54,7 +56,7 @@ rows.sort()
 t0 = rows[0][0]
 print(f"{len(rows)} events; total span {rows[-1][0] - t0} cycles")
 names = {16: "iss: dK(i-1) done -> load Q(i+1)", 17: "iss: wait P", 18: "iss: P ok -> dV", 19: "iss: dV done -> load dO(i+1)",
-         28: "cmp: P math done (wait dV(i-1))", 10: "iss: wait sfree", 11: "iss: sfree ok", 12: "iss: V ok -> dP", 13: "iss: dS(j-1) ok", 14: "iss: K ok -> S(j+1)", 15: "iss: dQ(j-1) issued",
+         28: "cmp: P math done (wait dV(i-1))", 10: "iss: wait sfree", 11: "iss: sfree ok", 12: "iss: dO ok -> dP", 13: "iss: dS(j-1) ok", 14: "iss: Q|K ok -> S(j+1)", 15: "iss: dQ(j-1) issued",
          20: "cmp: wait S", 21: "cmp: S ok", 22: "cmp: S in regs", 23: "cmp: P done, wait dP", 24: "cmp: dP ok", 25: "cmp: dS math done",
          26: "cmp: dS cols free", 27: "cmp: dS stored", 30: "iss: dQ(j-1) DONE", 31: "iss: dP issued", 32: "iss: dP DONE",
          33: "iss: S(j+1) issued", 34: "iss: S(j+1) DONE"}
