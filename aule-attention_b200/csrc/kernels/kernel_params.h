@@ -153,6 +153,12 @@ struct PagedCfg {
     static constexpr int TOK = 16;                              // tokens per pipeline stage (one MMA k-step of P.V)
     static constexpr int NS = (D == 128) ? 8 : 16;              // ring stages (K tile + V tile each)
     static constexpr int CONSUMERS = 4;                         // MMA/softmax warps; warp 4 is the TMA producer
+    // Tile i of a CTA lives in stage i % NS and belongs to warp i % CONSUMERS.  NS must be a multiple of CONSUMERS so
+    // that successive fills of a stage belong to the SAME warp: a warp then reaches "fill k of stage s" only after it
+    // consumed fill k-1, and its parity wait cannot be fooled by a fill that is still in flight (TMA tiles land out of
+    // order; with NS = 10 a warp saw "phase parity differs" on a stage whose previous fill had not landed yet and read
+    // stale data -- reproduced in tools/paged_ring_sim.py, then on the GPU).
+    static_assert(NS % CONSUMERS == 0, "ring stages must be a multiple of the consumer warps");
     static constexpr int THREADS = (CONSUMERS + 1) * 32;
     static constexpr uint32_t TILE_BYTES = TOK * D * 2;         // one K or V tile: [16 tokens][D/64 halves][128 B], 128B swizzle
     static constexpr uint32_t STAGE_BYTES = 2 * TILE_BYTES;

@@ -206,6 +206,7 @@ BWD_SHAPES = [
     (1, 2, 2, 100, 333, 128, False),    # cross attention, ragged Sk
     (1, 2, 1, 300, 129, 128, True),     # Sq > Sk causal
     (1, 2, 2, 64, 300, 64, True),       # keys beyond every query: dK = dV = 0 there
+    (1, 6, 2, 640, 640, 128, True),     # group of 3, five query blocks: the Q (3) and dO (2) rings wrap several times
     (2, 16, 16, 1024, 1024, 64, True),  # BASELINE.json configs[4]
 ]
 
@@ -254,6 +255,31 @@ def test_tensor_core_backward_agrees_with_cuda_core_backward(aule):
         finally:
             lib.aule_set_kernel_path(0)
     for a, b in zip(*grads):
+        assert (a - b).abs().max().item() / b.abs().max().item() <= 1e-2
+
+
+def test_backward_dkv_kernel_generations_agree(aule):
+    """The shipped dK/dV kernel (v4: transposed score tiles, P^T/dS^T in TMEM) against the v3 kernel it replaced
+    (P, dS staged through shared memory; aule_set_kernel_path bit 13) -- two independent data paths, same gradients."""
+    import torch
+    from aule import ffi
+    lib = ffi.load_library()
+    torch.manual_seed(5)
+    q = torch.randn(1, 8, 700, 128, device="cuda").to(torch.bfloat16)
+    k, v = (torch.randn(1, 2, 700, 128, device="cuda").to(torch.bfloat16) for _ in range(2))
+    do = torch.randn_like(q)
+    grads, kernels = [], []
+    for path in (0, 1 << 13):
+        lib.aule_set_kernel_path(path)
+        try:
+            tq, tk, tv = (t.clone().requires_grad_() for t in (q, k, v))
+            aule.flash_attention(tq, tk, tv, causal=True).backward(do)
+            torch.cuda.synchronize()
+            grads.append((tq.grad.float(), tk.grad.float(), tv.grad.float()))
+        finally:
+            lib.aule_set_kernel_path(0)
+    assert torch.equal(grads[0][0], grads[1][0])                       # dQ comes from the same kernel
+    for a, b in zip(grads[0][1:], grads[1][1:]):
         assert (a - b).abs().max().item() / b.abs().max().item() <= 1e-2
 
 
