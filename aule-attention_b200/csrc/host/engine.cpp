@@ -290,6 +290,7 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         const CUdeviceptr counter = d.sched + 4ull * (d.sched_next++ & 1023u);
         if (!(e = check(drv_.cuMemsetD32Async(counter, 0, 1, stream), "cuMemsetD32Async(scheduler counter)")).empty()) return e;
         p.sched_counter = (uint32_t*)counter;
+        p.cross_item = cross_item_enabled_ ? 1 : 0;
         const bool d128 = s.D == 128;
         const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
         const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)d.sm_count);

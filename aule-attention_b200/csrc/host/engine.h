@@ -116,7 +116,7 @@ public:
     // bit 9 (512) disables the L2-residency runs of the work-item order; bits 10-11 are a timing hook for the
     // backward (1: launch the dK/dV kernel only, 2: the dQ kernel only -- partial gradients, never for real use).
     void set_kernel_path(int32_t p) {
-        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 7; path_ = p & 255;
+        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 7; path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
     uint64_t launch_count() const { return launches_; }
@@ -138,6 +138,7 @@ private:
     int32_t path_ = kAuto;
     bool pair_heads_enabled_ = true;
     bool l2_runs_enabled_ = true;
+    bool cross_item_enabled_ = true;   // forward: next item's first Q K^T under the current item's last block (path bit 15 disables)
     int32_t bwd_order_ = 0;
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)

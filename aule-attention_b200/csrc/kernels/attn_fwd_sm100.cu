@@ -421,14 +421,30 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     mma_commit(bar(B_PVDONE + t));
                     if (last) mma_commit(bar(B_OFULL + t));
                 };
-                for (uint32_t w; get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w); ++it) {
+                // Cross-item pipelining: tile 0's softmax warps would otherwise sit idle from their last P of an item until
+                // the whole prologue of the next one has gone through the pipe.  In the LAST iteration of an item, right
+                // after PV_0, the next item is fetched and its QK_0(0) issued (its K_0 is the next tile of the load order,
+                // its Q_0 was requested when the last QK_0 of this item released the buffer), so S_0(0) of the next item
+                // is ready about one MMA group after tile 0 finished.
+                bool have_next = false, next_ok = false, qk0_done = false;
+                uint32_t w_next = 0, k_pre = 0;
+                for (uint32_t w;; ++it) {
+                    if (have_next) { w = w_next; if (!next_ok) break; }
+                    else if (!get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w)) break;
+                    have_next = false;
                     const Work wk = decode(p, w);
                     const uint32_t n0 = wk.n0, n1 = wk.n1;          // n0 <= n1, n1 >= 1
                     // ---- prologue: QK_0(0) QK_1(0) QK_0(1)
-                    uint32_t k_cur = acquire();                     // K_0
-                    mbar_wait(bar(B_QFULL + 0), it & 1);
-                    issue_qk(0, k_cur);
-                    if (n0 == 1) mma_commit(bar(B_QEMPTY + 0));
+                    uint32_t k_cur;
+                    if (qk0_done) {
+                        k_cur = k_pre;                              // K_0 acquired and QK_0(0) issued under the previous item
+                        qk0_done = false;
+                    } else {
+                        k_cur = acquire();                          // K_0
+                        mbar_wait(bar(B_QFULL + 0), it & 1);
+                        issue_qk(0, k_cur);
+                        if (n0 == 1) mma_commit(bar(B_QEMPTY + 0));
+                    }
                     mbar_wait(bar(B_QFULL + 1), it & 1);
                     issue_qk(1, k_cur);
                     if (n1 == 1) mma_commit(bar(B_QEMPTY + 1));
@@ -445,6 +461,18 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     for (uint32_t j = 0; j < n1; ++j) {
                         const uint32_t v = acquire();               // V_j
                         if (j < n0) issue_pv(0, v, j == 0, j == n0 - 1);
+                        if (j == n1 - 1 && p.cross_item) {          // last block: start the next item's tile 0
+                            next_ok = get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it + 1, w_next);
+                            have_next = true;
+                            if (next_ok) {
+                                const Work wn = decode(p, w_next);
+                                k_pre = acquire();                  // K_0 of the next item: next tile of the load order
+                                mbar_wait(bar(B_QFULL + 0), (it + 1) & 1);
+                                issue_qk(0, k_pre);
+                                if (wn.n0 == 1) mma_commit(bar(B_QEMPTY + 0));
+                                qk0_done = true;
+                            }
+                        }
                         if (j + 1 < n1) {
                             issue_qk(1, k_next);                    // QK_1(j+1): last user of K_{j+1}
                             if (j + 1 == n1 - 1) mma_commit(bar(B_QEMPTY + 1));

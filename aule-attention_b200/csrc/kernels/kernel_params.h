@@ -32,6 +32,7 @@ struct FwdParams {
                               // 0: 256 rows of one q-head
     uint32_t units_per_run;   // (batch, kv-head) units whose work items are scheduled together (L2 residency of K/V)
     uint32_t* sched_counter;  // zero-initialised per launch: next unclaimed work item (dynamic persistent scheduler)
+    int32_t cross_item;       // 1: the first Q K^T of the next work item is issued under the current item's last block
 };
 
 // v4 layout: Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
