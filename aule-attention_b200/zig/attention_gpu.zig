@@ -63,6 +63,22 @@ pub const AttentionEngine = struct {
         try p.dispatch(pc);
     }
 
+    /// attention_gpu.zig:484-653 forwardPaged: same tensors and result as forward(); the reference pages K/V into a
+    /// private block pool first, the B200 library runs the fused kernel on them directly.
+    pub fn forwardPaged(self: *AttentionEngine, q: *const cuda.GpuTensor, k: *const cuda.GpuTensor, v: *const cuda.GpuTensor, o: *const cuda.GpuTensor, causal: bool, window_size: i32) cuda.CudaError!void {
+        _ = self;
+        if (cuda.c.aule_attention_forward_paged(q.handle, k.handle, v.handle, o.handle, 0, 0, @intFromBool(causal), window_size) != 0)
+            return cuda.CudaError.ComputeFailed;
+    }
+
+    /// Serving-side paged KV cache (caller-owned block tables, vLLM layout): one query token per sequence.
+    /// q/out [B,Hq,D]; k_cache/v_cache [num_blocks, block_size, Hkv, D]; block_tables [B, max_blocks] i32; context_lens [B] i32.
+    pub fn pagedDecodeDevice(self: *AttentionEngine, dtype: cuda.DType, q: u64, k_cache: u64, v_cache: u64, block_tables: u64, context_lens: u64, out: u64, dims: struct { B: u32, Hq: u32, Hkv: u32, D: u32, num_blocks: u32, block_size: u32, max_blocks: u32, max_context: u32 }, scale: f32, window: i32, device: i32, stream: u64) cuda.CudaError!void {
+        _ = self;
+        if (cuda.c.aule_attention_paged_decode_dptr(q, k_cache, v_cache, block_tables, context_lens, out, dims.B, dims.Hq, dims.Hkv, dims.D, dims.num_blocks, dims.block_size, dims.max_blocks, dims.max_context, @intFromEnum(dtype), scale, window, device, stream) != 0)
+            return cuda.CudaError.ComputeFailed;
+    }
+
     /// attention_gpu.zig:707 forwardWithLse (host fp32 slices, MHA)
     pub fn forwardWithLse(self: *AttentionEngine, q: []const f32, k: []const f32, v: []const f32, o: []f32, lse: []f32, shape: [4]u32, causal: bool) cuda.CudaError!void {
         _ = self;
