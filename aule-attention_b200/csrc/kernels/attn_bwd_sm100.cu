@@ -462,10 +462,11 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
     const uint32_t bar_p = bar_dp + 8;                  // compute -> issuer: P^T(i) in TMEM (16 arrivals)
     const uint32_t bar_ds = bar_p + 8;                  // compute -> issuer: dS^T(i) in TMEM (16 arrivals)
     const uint32_t bar_done = bar_ds + 8;               // every MMA complete (commit)
+    const uint32_t bar_pb = bar_done + 24;              // compute -> issuer: second half of P^T(i) (bar_p announces the first half)
     const uint32_t bar_stat0 = bar_done + 8;            // publishers -> everyone: statistics of step s are in buffer s&1 (4 arrivals);
                                                         // one barrier per buffer, so a waiter can never be lapped (the next
                                                         // completion of ITS barrier needs its own dS^T arrival two steps on)
-    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 7) <= C::BAR_BYTES, "barrier area too small");
+    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 8) <= C::BAR_BYTES, "barrier area too small");
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
     float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [3][lse2 x128 | delta x128]
     const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO;
@@ -476,7 +477,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
         for (int i = 0; i < NQ; ++i) { mbar_init(bar_qfull0 + 8 * i, 1); mbar_init(bar_qfree0 + 8 * i, 1); }
         for (int i = 0; i < NDO; ++i) { mbar_init(bar_dofull0 + 8 * i, 1); mbar_init(bar_dofree0 + 8 * i, 1); }
         mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_done, 1);
-        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4);
+        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4); mbar_init(bar_pb, 16);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
@@ -574,16 +575,25 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             for (uint32_t step = 0; step < nsteps; ++step) {
                 const uint32_t qs_next = (qs == NQ - 1) ? 0 : qs + 1, qp_next = (qs == NQ - 1) ? (qp ^ 1) : qp;
                 const uint32_t ds_next = (ds_ == NDO - 1) ? 0 : ds_ + 1, dp_next = (ds_ == NDO - 1) ? (dp_ ^ 1) : dp_;
-                tr.ev(17, step);
-                wait(bar_p, step & 1);                                       // P^T(step) in TMEM
-                tr.ev(18, step);
-                tc_fence_after();
+                // dV += P^T dO (K = 128 queries, A = P^T in TMEM), in two halves: every thread publishes the first 16 of its
+                // 32 query columns (the even k-steps) before it computes the other 16, so half of dV runs under that math
+                // instead of after it -- dV gates S^T(step+1), the head of the next step's chain.
                 {
                     const uint32_t sdO = sdO0 + ds_ * C::TILE_BYTES;
+                    tr.ev(17, step);
+                    wait(bar_p, step & 1);                                   // first halves of P^T(step) in TMEM
+                    tr.ev(18, step);
+                    tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)                           // dV += P^T dO   (K = 128 queries, A = P^T in TMEM)
+                    for (int kk = 0; kk < 8; kk += 2)
                         mma_ts(tmem + COL_DV, tmem + COL_S + 32 * (kk >> 1) + 8 * (kk & 1),
                                mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128), ID_KMN, (step > 0 || kk > 0) ? 1u : 0u);
+                    wait(bar_pb, step & 1);                                  // second halves
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 1; kk < 8; kk += 2)
+                        mma_ts(tmem + COL_DV, tmem + COL_S + 32 * (kk >> 1) + 8 * (kk & 1),
+                               mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128), ID_KMN, 1u);
                     mma_commit(bar_dofree0 + 8 * ds_);
                 }
                 if (step + 1 < nsteps) {
@@ -671,33 +681,34 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 tr.ev(22, step);
                 const float2 cc = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(sc + 4 * e4);       // broadcast
-                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
-                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
-                    float2 v0, v1;
-                    if ((e4 & 1) == 0 || (p.order & 4)) { v0 = ex2_emu2(x0); } else { v0.x = ex2(x0.x); v0.y = ex2(x0.y); }   // 1 (A/B: 2) pair(s) in 4 on the FMA pipe
-                    v1.x = ex2(x1.x); v1.y = ex2(x1.y);
-                    pv[4 * e4] = v0.x; pv[4 * e4 + 1] = v0.y; pv[4 * e4 + 2] = v1.x; pv[4 * e4 + 3] = v1.y;
-                }
-                if (masked) {
+                for (int half = 0; half < 2; ++half) {               // 16 query columns each: publish, then the next 16
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const uint32_t q = q0 + e;
-                        pv[e] = (key_ok && q < p.Sq && !(diag && key > q)) ? pv[e] : 0.f;
+                    for (int e4 = 4 * half; e4 < 4 * half + 4; ++e4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(sc + 4 * e4);       // broadcast
+                        const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
+                        const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
+                        float2 v0, v1;
+                        if ((e4 & 1) == 0) { v0 = ex2_emu2(x0); } else { v0.x = ex2(x0.x); v0.y = ex2(x0.y); }   // 1 pair in 4 on the FMA pipe
+                        v1.x = ex2(x1.x); v1.y = ex2(x1.y);
+                        pv[4 * e4] = v0.x; pv[4 * e4 + 1] = v0.y; pv[4 * e4 + 2] = v1.x; pv[4 * e4 + 3] = v1.y;
                     }
-                }
-            }
-            tr.ev(28, step);
-            {
-                uint32_t pk[16];
+                    if (masked) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) pk[e] = pack2<BF16>(pv[2 * e], pv[2 * e + 1]);
-                tmem_st16(tS, pk);
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_p);
+                        for (int e = 16 * half; e < 16 * half + 16; ++e) {
+                            const uint32_t q = q0 + e;
+                            pv[e] = (key_ok && q < p.Sq && !(diag && key > q)) ? pv[e] : 0.f;
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) pk[e] = pack2<BF16>(pv[16 * half + 2 * e], pv[16 * half + 2 * e + 1]);
+                    tmem_st8(tS + 8 * half, pk);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(half ? bar_pb : bar_p);
+                    if (half == 0) tr.ev(28, step);
+                }
             }
             tr.ev(23, step);
             // ---- dS phase: dS^T = P^T o (dP^T - delta[query]) -> 16-bit, in place
