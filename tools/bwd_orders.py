@@ -1,7 +1,11 @@
 """Backward timing split on the GPU box: aule_attention_backward_dptr called directly (no autograd overhead) with the
-timing hook of aule_set_kernel_path bits 10-11 (0: whole backward, 1: Delta + dK/dV kernel only, 2: Delta + dQ kernel
-only), interleaved rounds, median.  TFLOP/s are always quoted on the whole backward's 2.5x-forward FLOPs, so only the
-mode-0 figure is a throughput; modes 1/2 show where the time goes.  usage: python tools/bwd_orders.py [rounds]"""
+hooks of aule_set_kernel_path: mode m is the path value m << 10.
+  0: whole backward       1: Delta + dK/dV kernel only       2: Delta + dQ kernel only   (bits 10-11; partial gradients)
+  +8 (path bit 13): the v3 dK/dV kernel (P, dS staged through shared memory) instead of the shipped transposed v4
+  32+m: mode m with path bit 9 set (L2-run CTA order hook; unused by the shipped backward)
+Interleaved rounds, median.  TFLOP/s are quoted on the whole backward's 2.5x-forward FLOPs, so only the mode-0 figure
+is a throughput; modes 1/2 show where the time goes.  For modes 8/16 the deviation of dq/dk/dv from mode 0 is reported.
+usage: AULE_BWD_ORDERS=0,1,2,8 python tools/bwd_orders.py [rounds]"""
 import json
 import os
 import statistics
