@@ -137,3 +137,26 @@ def test_public_surface_matches_reference():
     params = list(inspect.signature(aule.flash_attention).parameters)
     assert params == ["query", "key", "value", "rot_cos", "rot_sin", "causal", "scale", "window_size"]   # __init__.py:104
     from aule.vulkan import Aule, GpuTensor, AuleError  # noqa: F401  (reference import path)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/aule.h must compile as C99 (no C++-isms, no torch types) and a C program
+    must link against libaule.so and reach aule_get_error()/aule_version() without a GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "aule.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "t.c"
+    src.write_text('#include "aule.h"\n#include <stdio.h>\n#include <string.h>\n'
+                   'int main(void){ const char* v = aule_version(); const char* e = aule_get_error();\n'
+                   '  if (!v || !e) return 2; printf("%s|%s\\n", v, e);\n'
+                   '  return aule_attention_paged_decode_dptr(0,0,0,0,0,0,1,1,1,64,1,16,1,0,1,0.0f,-1,0,0) == -1 ? 0 : 3; }\n')
+    libdir = os.path.join(ROOT, "aule-attention_b200", "python", "aule", "lib")
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-laule", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "No error" in out.stdout or "|" in out.stdout
