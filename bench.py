@@ -292,7 +292,7 @@ def main():
         e2e = {"value": world * flops_rank * e_steps / dt / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": world * 2 * (q.numel() + k.numel() + v.numel()),
                "d2h_bytes_per_step": world * 2 * q.numel(), "steps": e_steps, "ms_per_step": 1e3 * dt / e_steps,
-               "api": "aule_attention_forward_host (pinned host buffers, 8-way chunked H2D/compute/D2H overlap)"}
+               "api": "aule_attention_forward_host (pinned host buffers, chunked H2D/compute/D2H overlap on three streams)"}
 
     if rank != 0:
         if dist is not None:
