@@ -115,6 +115,14 @@ def test_no_cpu_fallback():
         aule.flash_attention(q, q, q)
     with pytest.raises(aule.AuleError):
         aule.Aule()
+    import torch
+    with pytest.raises(RuntimeError, match="no CPU fallback"):          # paged decode and RoPE entries too
+        aule.flash_attention_paged(torch.zeros(1, 2, 64), torch.zeros(2, 16, 2, 64), torch.zeros(2, 16, 2, 64),
+                                   torch.zeros(1, 2, dtype=torch.int32), torch.ones(1, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        aule.flash_attention_rope(torch.zeros(1, 2, 8, 16), torch.zeros(1, 2, 8, 16), torch.zeros(1, 2, 8, 16),
+                                  torch.ones(8, 8), torch.zeros(8, 8))
+    assert aule.flash_attention_paged_amd is aule.flash_attention_paged   # the name the reference exports
 
 
 def test_product_path_never_imports_oracle():
