@@ -112,9 +112,13 @@ public:
     std::string copy_d2h(int dev, void* dst, CUdeviceptr src, size_t bytes);
     std::string synchronize(int dev);
 
-    // path: 0 auto, 1 force CUDA-core kernels, 16+v tuning variant v; bit 8 (256) disables head pairing,
-    // bit 9 (512) disables the L2-residency runs of the work-item order; bits 10-11 are a timing hook for the
-    // backward (1: launch the dK/dV kernel only, 2: the dQ kernel only -- partial gradients, never for real use).
+    // path (test / A-B hooks; 0 = the shipped configuration):
+    //   bits 0-7   0 auto, 1 force the CUDA-core kernels, 16+v forward tuning variant v (bf16)
+    //   bit 8      forward: no head pairing                     bit 9   forward: no L2-residency runs of the work-item order
+    //   bits 10-11 backward timing hook: 1 = dK/dV kernel only, 2 = dQ kernel only (partial gradients, never for real use)
+    //   bit 12     backward bring-up: the issuer waits for every MMA group (tools/bwd_trace.py serial)
+    //   bit 13     backward: the v3 dK/dV kernel (P, dS staged through shared memory) instead of the transposed v4
+    //   bit 15     forward: no cross-item prefetch of the next work item's first Q K^T
     void set_kernel_path(int32_t p) {
         pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 7; path_ = p & 255;
     }

@@ -206,7 +206,9 @@ AULE_API uint64_t aule_launch_count(void);
 AULE_API const char* aule_last_kernel(void);
 /* Test hooks. aule_set_kernel_path: 0 = automatic choice, 1 = force the CUDA-core
  * (fp32-accumulate) kernels for every dtype -- used to cross-check the tensor-core kernel
- * on the GPU itself.  aule_smoke_multiply: out[i] = 2*in[i] through the whole
+ * on the GPU itself; higher bits select A/B variants of the tensor-core kernels (forward tuning
+ * variants, head pairing, L2 runs, cross-item prefetch, backward kernel generation / timing split;
+ * the bit map is in csrc/host/engine.h, Engine::set_kernel_path).  aule_smoke_multiply: out[i] = 2*in[i] through the whole
  * module-load / launch / copy path (the tests/test_multiply.zig analogue,
  * src/compute_pipeline.zig:203-254 + shaders/test.comp). */
 AULE_API int32_t aule_set_kernel_path(int32_t path);
