@@ -130,15 +130,19 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.bwd_dq_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)aule_kp::BwdDqCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d128)");
     }
-    for (int dd = 0; dd < 2 && e.empty(); ++dd)
-        for (int v = 0; v < 3 && e.empty(); ++v) {
+    // tuning builds only: optional symbols
+    for (int dd = 0; dd < 2; ++dd) {
+        for (int v = 0; v < 3; ++v) {
             const std::string nm = std::string("aule_fwd_sm100_bf16_d") + (dd ? "128" : "64") + "_e" + char('0' + v);
-            e = get(&d.fwd_sm100_var[dd][v], nm);
-            if (e.empty())
-                e = check(drv_.cuFuncSetAttribute(d.fwd_sm100_var[dd][v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                                  dd ? (int)FwdCfg<128>::SMEM_BYTES : (int)FwdCfg<64>::SMEM_BYTES),
-                          "cuFuncSetAttribute(smem variant)");
+            if (drv_.cuModuleGetFunction(&d.fwd_sm100_var[dd][v], d.mod, nm.c_str()) != CUDA_SUCCESS) { d.fwd_sm100_var[dd][v] = nullptr; continue; }
+            drv_.cuFuncSetAttribute(d.fwd_sm100_var[dd][v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                    dd ? (int)FwdCfg<128>::SMEM_BYTES : (int)FwdCfg<64>::SMEM_BYTES);
         }
+        const std::string nm4 = std::string("aule_fwd4_sm100_bf16_d") + (dd ? "128" : "64");
+        if (drv_.cuModuleGetFunction(&d.fwd4_sm100[dd], d.mod, nm4.c_str()) != CUDA_SUCCESS) d.fwd4_sm100[dd] = nullptr;
+        else drv_.cuFuncSetAttribute(d.fwd4_sm100[dd], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                     dd ? (int)aule_kp::FwdCfg4<128>::SMEM_BYTES : (int)aule_kp::FwdCfg4<64>::SMEM_BYTES);
+    }
     for (int t = 0; t < 3 && e.empty(); ++t) e = get(&d.rope[t], std::string("aule_rope_") + kDtypeSuffix[t]);
     for (int t = 1; t < 3 && e.empty(); ++t) {
         e = get(&d.paged[t][0], std::string("aule_paged_sm100_") + kDtypeSuffix[t] + "_d64");
@@ -291,19 +295,27 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         if (!(e = check(drv_.cuMemsetD32Async(counter, 0, 1, stream), "cuMemsetD32Async(scheduler counter)")).empty()) return e;
         p.sched_counter = (uint32_t*)counter;
         p.cross_item = cross_item_enabled_ ? 1 : 0;
+        p.trace = (unsigned long long*)trace_;
         const bool d128 = s.D == 128;
-        const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
         const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)d.sm_count);
-        void* params[] = {&tmQ, &tmK, &tmV, &tmO, &p};
         char name[64];
+        if (fwd_v4_) {                     // A/B hook (tuning builds): the v4 kernel, TMA-stored output
+            if (dtype != kBF16 || !d.fwd4_sm100[d128 ? 1 : 0]) return "the v4 forward kernel is only present in tuning builds (bf16)";
+            void* params4[] = {&tmQ, &tmK, &tmV, &tmO, &p};
+            snprintf(name, sizeof(name), "aule_fwd4_sm100_bf16_d%u", s.D);
+            return launch(d, d.fwd4_sm100[d128 ? 1 : 0], name, grid, 1, 1, 512,
+                          d128 ? aule_kp::FwdCfg4<128>::SMEM_BYTES : aule_kp::FwdCfg4<64>::SMEM_BYTES, stream, params4);
+        }
+        const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
+        void* params[] = {&tmQ, &tmK, &tmV, &p};
         snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
         CUfunction fn = d.fwd_sm100[dtype][d128 ? 1 : 0];
-        unsigned smem_use = smem;
-        if (path_ >= kVariantBase && path_ < kVariantBase + 3 && dtype == kBF16 && d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase]) {
+        if (path_ >= kVariantBase && path_ < kVariantBase + 3) {
+            if (dtype != kBF16 || !d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase]) return "forward tuning variants are only present in tuning builds (bf16)";
             fn = d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase];
             snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d%u_e%d", s.D, path_ - kVariantBase);
         }
-        return launch(d, fn, name, grid, 1, 1, 512, smem_use, stream, params);
+        return launch(d, fn, name, grid, 1, 1, 512, smem, stream, params);
     }
     SimtParams p;
     memset(&p, 0, sizeof(p));

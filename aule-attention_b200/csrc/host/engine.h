@@ -43,7 +43,9 @@ struct Device {
     CUfunction bwd_dq_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dkv_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
-    CUfunction fwd_sm100_var[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // bf16 tuning variants [D==128][v]
+    // present only in tuning builds (make EXTRA_NVFLAGS=-DAULE_TUNING_VARIANTS): bf16 variants [D==128][v] and the v4 kernel
+    CUfunction fwd_sm100_var[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    CUfunction fwd4_sm100[2] = {nullptr, nullptr};
     CUfunction bwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     CUfunction bwd_dkvt_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // transposed dK/dV kernel (v4)
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
@@ -118,9 +120,10 @@ public:
     //   bits 10-11 backward timing hook: 1 = dK/dV kernel only, 2 = dQ kernel only (partial gradients, never for real use)
     //   bit 12     backward bring-up: the issuer waits for every MMA group (tools/bwd_trace.py serial)
     //   bit 13     backward: the v3 dK/dV kernel (P, dS staged through shared memory) instead of the transposed v4
-    //   bit 15     forward: no cross-item prefetch of the next work item's first Q K^T
+    //   bit 14     forward: the v4 kernel (tuning builds only; an error otherwise)
+    //   bit 15     forward v4: no cross-item prefetch of the next work item's first Q K^T
     void set_kernel_path(int32_t p) {
-        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 7; path_ = p & 255;
+        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
     uint64_t launch_count() const { return launches_; }
@@ -144,6 +147,7 @@ private:
     bool l2_runs_enabled_ = true;
     bool cross_item_enabled_ = true;   // forward: next item's first Q K^T under the current item's last block (path bit 15 disables)
     int32_t bwd_order_ = 0;
+    int32_t fwd_v4_ = 0;
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)
     uint64_t trace_ = 0;

@@ -1,4 +1,5 @@
-// Fused FlashAttention-2 forward for sm_100a (B200): TMA -> SMEM -> tcgen05.mma -> TMEM.   (kernel v5, "stream")
+// Fused FlashAttention-2 forward for sm_100a (B200), kernel v4: superseded by v5 (attn_fwd_sm100.cu); compiled only
+// into tuning builds (-DAULE_TUNING_VARIANTS) as aule_fwd4_sm100_* for A/B runs (aule_set_kernel_path bit 14).
 //
 // Replaces (behaviour, not code) the reference's forward kernels:
 //   python/aule/triton_flash.py:62-235 (_flash_attn_fwd_kernel),
@@ -6,38 +7,31 @@
 // Semantics kept: O = softmax(scale*QK^T + mask) V; top-left causal mask (j <= i,
 // triton_flash.py:187); GQA kv_head = q_head / (Hq/Hkv) (:95-96); LSE = m + ln(l) (:232).
 //
-// One persistent CTA per SM (512 threads).  A work item is two 128-row query tiles that share their K/V blocks
-// (GQA: the two q-heads 2h, 2h+1 of a KV group at the same 128 rows; otherwise 256 rows of one head).
+// One persistent CTA per SM (512 threads) looping over work items (256 query rows = two
+// 128-row tiles of one (batch, q-head)), heaviest first, dealt in snake order:
 //
 //   warps 0-3   softmax, tile 0   (thread == query row: S TMEM -> registers, exp2, P -> TMEM)
 //   warps 4-7   softmax, tile 1
-//   warps 8-11  epilogue          (O: TMEM -> regs -> 1/l -> 256-bit global stores; LSE)
+//   warps 8-11  epilogue          (O: TMEM -> regs -> 1/l -> SMEM -> TMA store; LSE)
 //   warp  12    MMA issuer        (one elected thread issues every tcgen05.mma)
-//   warp  13    scheduler + TMA producer (one elected thread claims work items and issues every bulk tensor load)
+//   warp  13    TMA producer      (one elected thread issues every bulk tensor load)
 //   warp  14    TMEM allocator
-//
-// What v5 changes over v4 (attn_fwd_sm100_v4.cu): the K/V blocks of ALL work items a CTA processes form one
-// continuous stream of "slots".  The MMA thread, the TMA thread and the softmax warps walk that stream with
-// cursors that cross work-item boundaries, so the steady-state issue order
-//     PV_0(i)  QK_1(i+1)  PV_1(i)  QK_0(i+2)
-// never drains at an item boundary: while the last blocks of item k are still in the softmax / PV stages, the first
-// Q K^T of item k+1 (both tiles) are already issued.  v4 lost ~1.5 block times of the ping-pong per item
-// (16.5 blocks per item on config C).  That needs (a) Q tiles of two items resident at once: a 3-slot Q ring
-// (tile x of item k lives in slot (2k + x) mod 3), paid for by dropping the O staging tile -- the epilogue now
-// stores O straight from registers with 256-bit global stores (a thread owns a row: 32-byte sectors are written
-// whole); (b) the scheduler claiming items ahead of use: an 8-slot ring of DECODED work descriptors in shared
-// memory (no role re-derives the item geometry; the decode's integer divisions are paid once, by the producer).
 //
 // TMEM (512 columns): S [0,128) shared by both tiles | P0 [128,192) | P1 [192,256) |
 //                     O0 [256,256+D) | O1 [256+D,256+2D).
-// S only lives from the end of Q K^T until the softmax warps have copied it to registers, so ONE S buffer serves
-// both tiles and P gets columns of its own; the next Q K^T of a tile is issued as soon as the OTHER tile's softmax
-// has drained S.  Hazards: P_t is rewritten for the next block only after pv_done[t]; the rare in-place O_t rescale
-// waits for the same barrier; S is handed over through s_free; O_t is handed to the epilogue at the last PV of an
-// item (o_full) and back before the first PV of the next (o_empty).
+// S only lives from the end of Q K^T until the softmax warps have copied it to registers
+// (~150 cycles), so ONE S buffer serves both tiles and P gets columns of its own.  That removes the
+// S/P aliasing of v3 and with it the serial chain  softmax(j) -> P V -> Q K^T(j+1) -> softmax(j+1):
+// the next Q K^T of a tile is issued as soon as the OTHER tile's softmax has drained S, and runs
+// under this tile's exp phase, so the softmax warps (the MUFU-bound stage) never wait for it.
+// Steady-state issue order of the MMA thread (all waits blocking, order == readiness order):
+//     PV_0(j)  QK_1(j+1)  PV_1(j)  QK_0(j+2)  PV_0(j+1)  QK_1(j+2)  ...
+// Hazards: P_t is rewritten for block j+1 only after pv_done[t] (commit after PV_t(j)); the rare
+// in-place O_t rescale waits for the same barrier; S is handed over through s_free (128 arrivals
+// after the tcgen05.ld of S completes).
 //
-// SMEM (D=128): Q ring 3x32 KB | K/V ring 4x32 KB (load order K0 K1 V0 K2 V1 K3 ..., continuous across items) |
-// row statistics 2 KB | work descriptors | mbarriers.  All operand tiles are [128 rows][64 elements] 128B-swizzled
+// SMEM (D=128): Q 2x32 KB | K/V ring 4x32 KB (load order K0 K1 V0 K2 V1 K3 ...) | O staging 32 KB |
+// row statistics 2 KB | mbarriers.  All operand tiles are [128 rows][64 elements] 128B-swizzled
 // sub-tiles (TMA box 64x128): the K-major canonical UMMA layout for Q/K and the MN-major one for V.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -45,33 +39,31 @@
 #include "sm100_ptx.cuh"
 #include "kernel_params.h"
 
-namespace fwd100 {
+namespace fwd100v4 {
 using namespace sm100;
 using aule_kp::FwdParams;
-template <int D> using Cfg = aule_kp::FwdCfg<D>;
+template <int D> using Cfg = aule_kp::FwdCfg4<D>;
 
-// barrier indices
+// barrier indices (pairs are indexed by tile)
 enum : int {
-    B_QFULL = 0,     // [3] TMA -> MMA: Q ring slot landed
-    B_QEMPTY = 3,    // [3] MMA -> TMA: last Q K^T that reads the slot is done (commit)
-    B_SFULL = 6,     // [2] MMA -> softmax t: S holds Q_t K^T (commit)
-    B_PFULL = 8,     // [2] softmax t -> MMA: P_t columns [0,48) written (keys 0..95)
-    B_PFULLB = 10,   // [2] softmax t -> MMA: P_t columns [48,64) written (keys 96..127)
-    B_PVDONE = 12,   // [2] MMA -> softmax t: PV_t complete (commit): P_t / O_t may be touched
-    B_OFULL = 14,    // [2] MMA -> epilogue: last PV_t of the work item done (commit)
-    B_OEMPTY = 16,   // [2] epilogue -> MMA: O_t drained from TMEM
-    B_STFULL = 18,   // [2] softmax t -> epilogue: row statistics written
-    B_STEMPTY = 20,  // [2] epilogue -> softmax t: row statistics consumed
-    B_SFREE = 22,    // softmax (either tile) -> MMA: S copied to registers
-    B_WKFULL = 23,   // [8] scheduler -> all roles: work descriptor slot published
-    B_WKEMPTY = 31,  // [8] all roles -> scheduler: slot consumed (1 MMA + 256 softmax + 128 epilogue arrivals)
-    B_KVFULL = 39    // [NS] full, then [NS] empty
+    B_QFULL = 0,     // TMA -> MMA: Q_t landed
+    B_QEMPTY = 2,    // MMA -> TMA: last QK_t of the work item done (commit)
+    B_SFULL = 4,     // MMA -> softmax t: S holds Q_t K^T (commit)
+    B_PFULL = 6,     // softmax t -> MMA: P_t columns [0,48) written (keys 0..95)
+    B_PFULLB = 8,    // softmax t -> MMA: P_t columns [48,64) written (keys 96..127)
+    B_PVDONE = 10,   // MMA -> softmax t: PV_t(j) complete (commit): P_t / O_t may be touched
+    B_OFULL = 12,    // MMA -> epilogue: last PV_t of the work item done (commit)
+    B_OEMPTY = 14,   // epilogue -> MMA: O_t drained from TMEM
+    B_STFULL = 16,   // softmax t -> epilogue: row statistics written
+    B_STEMPTY = 18,  // epilogue -> softmax t: row statistics consumed
+    B_SFREE = 20,    // softmax (either tile) -> MMA: S copied to registers
+    B_WKFULL = 21,   // scheduler -> all roles: work_ring[slot] holds the next work item (4 slots)
+    B_WKEMPTY = 25,  // all roles -> scheduler: slot consumed (1 MMA + 256 softmax + 128 epilogue arrivals)
+    B_KVFULL = 29    // + NS: kv_empty
 };
-constexpr int WK_SLOTS = 8;
 
 struct Work {
-    uint32_t bh, bkv, row0, n0;
-    uint32_t n1;                 // 0 = stop sentinel
+    uint32_t bh, bkv, row0, n0, n1;
     uint32_t j0;                 // first K/V block (left edge of a sliding window; 0 otherwise)
     uint32_t dbh, drow;          // tile t covers q-head (bh + t*dbh), rows [row0 + t*drow, +128)
 };
@@ -79,9 +71,10 @@ struct Work {
 // Work items.  A "unit" is one (batch, kv-head) with the Hq/Hkv query heads that share it.  Units are scheduled in
 // runs of `units_per_run` (chosen by the host so that a run's K/V stays L2-resident: without it every unit is in
 // flight at once and K/V is re-fetched from HBM for every query block -- measured 1.65 GB of DRAM reads per
-// config-C launch against 0.40 GB compulsory).  Inside a run items go heaviest-first (causal).
+// config-C launch against 0.40 GB compulsory).  Inside a run items go heaviest-first (causal), so the snake
+// deal below balances every run on its own.
 //  pair_heads: item = 128 query rows x the two q-heads (2h, 2h+1) of the unit -> both tiles walk the same K/V
-//              blocks and have EQUAL trip counts.
+//              blocks and have EQUAL trip counts (no idle slot for tile 0).
 //  otherwise : item = 256 query rows of one q-head (tile 1 needs one more block than tile 0 under causal).
 __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     Work t;
@@ -117,25 +110,16 @@ __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     return t;
 }
 
-// Work descriptors travel through an 8-slot ring in shared memory (32 bytes each), written by the scheduler thread.
-__device__ __forceinline__ void ring_write(uint32_t ring_smem, uint32_t slot, const Work& w) {
-    const uint32_t a = ring_smem + slot * 32;
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w.bh), "r"(w.bkv), "r"(w.row0), "r"(w.n0) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(w.n1), "r"(w.j0), "r"(w.dbh), "r"(w.drow) : "memory");
-}
-__device__ __forceinline__ Work ring_read(uint32_t ring_smem, uint32_t slot) {
-    Work w;
-    const uint32_t a = ring_smem + slot * 32;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.bh), "=r"(w.bkv), "=r"(w.row0), "=r"(w.n0) : "r"(a) : "memory");
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.n1), "=r"(w.j0), "=r"(w.dbh), "=r"(w.drow) : "r"(a + 16) : "memory");
-    return w;
-}
-// Consumer side: wait until item `it` of this CTA has been published, copy it.  false = stop sentinel.
-__device__ __forceinline__ bool fetch_work(uint32_t bar_full0, uint32_t ring_smem, uint32_t it, Work& w) {
-    const uint32_t slot = it & (WK_SLOTS - 1);
-    mbar_wait(bar_full0 + 8 * slot, (it / WK_SLOTS) & 1);
-    w = ring_read(ring_smem, slot);
-    return w.n1 != 0;
+// Dynamic persistent schedule: the TMA-producer thread claims work items with an atomic counter (items are sorted
+// run by run, heaviest first inside a run, see decode) and publishes them through a 4-slot ring in shared memory;
+// every other role consumes the ring in order.  A claimed index >= num_tiles is the stop sentinel.
+__device__ __forceinline__ bool get_work(const FwdParams& p, uint32_t bar_full0, uint32_t bar_empty0,
+                                         const volatile uint32_t* ring, uint32_t it, uint32_t& w) {
+    const uint32_t slot = it & 3;
+    mbar_wait(bar_full0 + 8 * slot, (it >> 2) & 1);
+    w = ring[slot];
+    mbar_arrive(bar_empty0 + 8 * slot);
+    return w < p.num_tiles;
 }
 
 struct Ring {
@@ -145,44 +129,25 @@ struct Ring {
     }
 };
 
-// Bring-up tracer (aule_set_trace_buffer + kernel variant "_tr"): CTA 0 records (tag << 48 | clock64) events,
-// one region of 4096 entries per traced thread (0 MMA issuer, 1 / 2 softmax tile 0 / 1 row 0, 3 TMA producer).
-template <bool ON>
-struct Tracer {
-    unsigned long long* buf = nullptr;
-    uint32_t n = 0;
-    __device__ __forceinline__ Tracer(unsigned long long* base, uint32_t region, bool on) {
-        if constexpr (ON) buf = (base && on && blockIdx.x == 0) ? base + region * 4096 : nullptr;
-    }
-    __device__ __forceinline__ void ev(uint32_t code, uint32_t step) {
-        if constexpr (ON) {
-            if (buf && n < 4096) buf[n++] = ((unsigned long long)((code << 8) | (step & 255u)) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
-        }
-    }
-};
-
-template <int D, bool BF16, int EMU4, bool TRUNC_PACK, bool TRACE>
+template <int D, bool BF16, int EMU4, bool TRUNC_PACK, uint32_t HOT_HINT>
 __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
-                                         const FwdParams& p) {
+                                         const CUtensorMap* tmO, const FwdParams& p) {
     using C = Cfg<D>;
     constexpr int NS = C::NS;
-    constexpr uint32_t HOT_HINT = 1000000u;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sb = smem_u32(smem);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int i) -> uint32_t { return sb + C::OFF_BAR + 8u * i; };
     float* sStat = reinterpret_cast<float*>(smem + C::OFF_STAT);          // [l0 | l1 | m0 | m1] x 128
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
-    const uint32_t wring = sb + C::OFF_WORK;
+    volatile uint32_t* work_ring = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_WORK);
 
     if (threadIdx.x == 0 && (sb & 1023u)) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
 
     if (warp == 13 && lane == 0) {
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(bar(B_QFULL + i), 1);     // TMA tx
-            mbar_init(bar(B_QEMPTY + i), 1);    // tcgen05.commit
-        }
         for (int t = 0; t < 2; ++t) {
+            mbar_init(bar(B_QFULL + t), 1);     // TMA tx
+            mbar_init(bar(B_QEMPTY + t), 1);    // tcgen05.commit
             mbar_init(bar(B_SFULL + t), 1);     // tcgen05.commit
             mbar_init(bar(B_PFULL + t), 128);   // softmax threads
             mbar_init(bar(B_PFULLB + t), 128);  // softmax threads
@@ -193,7 +158,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             mbar_init(bar(B_STEMPTY + t), 128); // epilogue threads
         }
         mbar_init(bar(B_SFREE), 128);           // softmax threads of whichever tile owns S
-        for (int i = 0; i < WK_SLOTS; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(bar(B_WKFULL + i), 1);     // scheduler (TMA thread)
             mbar_init(bar(B_WKEMPTY + i), 385);  // 1 MMA + 256 softmax + 128 epilogue threads
         }
@@ -202,7 +167,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             mbar_init(bar(B_KVFULL + NS + s), 1);
         }
         fence_mbar_init();
-        tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV);
+        tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmO);
     }
     if (warp == 14) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
@@ -217,26 +182,22 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 
     if (warp < 8) {
         // ===================================================== softmax warps
-        reg_inc<C::REGS_SOFTMAX>();
+        reg_inc<192>();
         const uint32_t t = warp >> 2;                               // tile 0 / 1
         const uint32_t r = (warp & 3) * 32 + lane;                  // row within the tile == TMEM lane
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
         const uint32_t tS = tmem + lane_addr + C::COL_S;
         const uint32_t tP = tmem + lane_addr + (t ? C::COL_P1 : C::COL_P0);
         const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
-        Tracer<TRACE> tr(p.trace, 1 + t, (warp & 3) == 0 && lane == 0);
         uint32_t g = 0, it = 0;                                     // g: blocks processed so far by this tile
-        Work wk;
-        for (; fetch_work(bar(B_WKFULL), wring, it, wk); ++it) {
-            mbar_arrive(bar(B_WKEMPTY + (it & (WK_SLOTS - 1))));    // descriptor copied to registers
+        for (uint32_t w; get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w); ++it) {
+            const Work wk = decode(p, w);
             const uint32_t n = t ? wk.n1 : wk.n0;
             const uint32_t trow0 = wk.row0 + t * wk.drow;
             const uint32_t grow = trow0 + r;                        // global query row
             float m_used = -INFINITY, l = 0.f;
             for (uint32_t j = 0; j < n; ++j, ++g) {
-                tr.ev(10, g);
                 mbar_wait<HOT_HINT>(bar(B_SFULL + t), g & 1);
-                tr.ev(11, g);
                 tc_fence_after();
                 uint32_t s[4][32];
 #pragma unroll
@@ -244,7 +205,6 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(bar(B_SFREE));                          // S may be overwritten by the next Q K^T
-                tr.ev(12, g);
                 const uint32_t jg = wk.j0 + j;                      // global K/V block index
                 const bool win_edge = p.window > 0 && jg * 128 + (uint32_t)p.window < trow0 + 128;   // some key left of a row's window
                 const bool need_mask = (p.causal && jg * 128 + 127 > trow0) || ((jg + 1) * 128 > p.Sk) || win_edge;
@@ -279,7 +239,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
                 // Lazy rescale: adopt the new maximum only when it grew by more than 2^8 in the
                 // exp2 domain; otherwise P stays <= 256, harmless in bf16/fp16 and fp32 sums.
-                const bool grow_max = (m_new - m_used) * p.scale_log2 > 8.f;   // m_used = -inf -> true (unless m_new = -inf too: NaN -> false)
+                const bool grow_max = (m_new - m_used) * p.scale_log2 > 8.f;   // m_used = -inf -> true
                 bool pv_waited = false;
                 if (__any_sync(0xffffffffu, grow_max)) {
                     const float alpha = grow_max ? ex2((m_used - m_new) * p.scale_log2) : 1.f;
@@ -300,7 +260,6 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         }
                     }
                 }
-                tr.ev(13, g);
                 // bf16: P is packed by TRUNCATION (one PRMT instead of the quarter-rate F2FP); the exponent carries
                 // +log2(1+2^-9) so that the truncated values are unbiased, and l is corrected by the same factor.
                 const float neg_ms = ((m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2) + ((BF16 && TRUNC_PACK) ? 0.0028150156f : 0.f);
@@ -327,9 +286,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     if (c == 1) {
                         // P_t is still being read by PV_t of the previous block until pv_done: the first
                         // two chunks are computed under that MMA and stored once it has finished.
-                        tr.ev(14, g);
                         if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
-                        tr.ev(15, g);
                         tc_fence_after();
                         tmem_st16(tP, pk[0]);
                         tmem_st16(tP + 16, pk[1]);
@@ -338,46 +295,43 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(bar(B_PFULL + t));
-                        tr.ev(16, g);
                     } else if (c == 3) {
                         tmem_st16(tP + 48, pk[1]);
                         tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(bar(B_PFULLB + t));
-                        tr.ev(17, g);
                     }
                 }
                 const float2 acc = __fadd2_rn(acc0, acc1);
                 l += acc.x + acc.y;
             }
-            // hand the row statistics to the epilogue warps; a row that saw no visible key reports l = 0
+            // hand the row statistics to the epilogue warps
             mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
-            sStat[t * 128 + r] = (m_used == -INFINITY) ? 0.f : ((BF16 && TRUNC_PACK) ? l * (1.f / 1.001953125f) : l);   // undo the 1+2^-9 bias carried by the exponents
+            sStat[t * 128 + r] = (BF16 && TRUNC_PACK) ? l * (1.f / 1.001953125f) : l;   // undo the 1+2^-9 bias carried by the exponents
             sStat[256 + t * 128 + r] = m_used;
             mbar_arrive(bar(B_STFULL + t));
         }
     } else if (warp < 12) {
         // ===================================================== epilogue warps
-        reg_dec<C::REGS_EPILOGUE>();
+        reg_dec<64>();
         const uint32_t r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
+        const bool issuer = (warp == 8 && lane == 0);
+        const uint32_t sO = sb + C::OFF_O;
         uint32_t it = 0;
-        Work wk;
-        for (; fetch_work(bar(B_WKFULL), wring, it, wk); ++it) {
-            mbar_arrive(bar(B_WKEMPTY + (it & (WK_SLOTS - 1))));
+        for (uint32_t w; get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w); ++it) {
+            const Work wk = decode(p, w);
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
                 mbar_wait(bar(B_STFULL + t), it & 1);
                 const float l = sStat[t * 128 + r];
                 const float m = sStat[256 + t * 128 + r];
                 mbar_arrive(bar(B_STEMPTY + t));
-                const uint32_t grow = wk.row0 + t * wk.drow + r;
-                const bool row_ok = grow < p.Sq;
-                const size_t orow = (size_t)(wk.bh + t * wk.dbh) * p.Sq + grow;
-                uint8_t* optr = reinterpret_cast<uint8_t*>(p.o) + orow * (size_t)(D * 2);
-                const float inv = (l > 0.f) ? 1.f / l : 0.f;        // rows without a visible key: O = 0, LSE = -inf
                 mbar_wait(bar(B_OFULL + t), it & 1);
                 tc_fence_after();
+                if (issuer) tma_store_wait_read<0>();               // the previous store has finished reading sO
+                named_bar_sync(1, 128);
+                const float inv = 1.f / l;
 #pragma unroll
                 for (int c = 0; c < D / 32; ++c) {
                     uint32_t o[32];
@@ -387,66 +341,58 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         tc_fence_before();
                         mbar_arrive(bar(B_OEMPTY + t));
                     }
-                    // 32 fp32 -> 32 x 16-bit = 64 B of this row: two 256-bit stores (whole 32-byte sectors)
-                    uint32_t v[16];
+                    // 32 fp32 -> 32 x 16-bit = 64 B = 4 swizzled 16-byte units of this row
+                    const uint32_t chunk = (c * 32) / 64, unit0 = ((c * 32) % 64) / 8;
+                    const uint32_t rowbase = sO + chunk * C::CHUNK_BYTES + r * 128;
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) v[u] = pack2<BF16>(__uint_as_float(o[2 * u]) * inv, __uint_as_float(o[2 * u + 1]) * inv);
-                    if (row_ok) {
-                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr + c * 64),
-                                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr + c * 64 + 32),
-                                     "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t v0 = pack2<BF16>(__uint_as_float(o[8 * u + 0]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
+                        const uint32_t v1 = pack2<BF16>(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
+                        const uint32_t v2 = pack2<BF16>(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
+                        const uint32_t v3 = pack2<BF16>(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
+                        const uint32_t addr = rowbase + (((unit0 + u) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
                     }
                 }
-                if (p.lse != nullptr && row_ok)
-                    p.lse[orow] = (l > 0.f) ? m * p.scale + __logf(l) : -INFINITY;   // LSE = m + ln(l)
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (issuer) {
+#pragma unroll
+                    for (int c = 0; c < C::CHUNKS; ++c)
+                        tma_store_3d(tmO, sO + c * C::CHUNK_BYTES, c * 64, (int32_t)(wk.row0 + t * wk.drow), (int32_t)(wk.bh + t * wk.dbh));
+                    tma_store_commit();
+                }
+                const uint32_t grow = wk.row0 + t * wk.drow + r;
+                if (p.lse != nullptr && grow < p.Sq)
+                    p.lse[(size_t)(wk.bh + t * wk.dbh) * p.Sq + grow] = m * p.scale + __logf(l);   // LSE = m + ln(l)
             }
         }
+        if (issuer) tma_store_wait_all<0>();
     } else {
-        reg_dec<C::REGS_OTHER>();
+        reg_dec<64>();
         if (warp == 12) {
             // ================================================= MMA issuer
             if (elect_one()) {
-                Tracer<TRACE> tr(p.trace, 0, true);
                 Ring ring;                                          // next K/V ring slot to acquire
                 uint32_t gpv0 = 0, gpv1 = 0;                        // PV_t issued so far (parity of p_full / p_fullb)
                 uint32_t nqk = 0;                                   // Q K^T issued so far (parity of s_free)
+                uint32_t it = 0;
                 // Descriptors are (constant high word, low word = const | addr>>4); stepping along K
                 // is an immediate add on the low word (the 14-bit address field never carries).
                 constexpr uint32_t HI_K_HI = uint32_t(HI_K >> 32), HI_K_LO = uint32_t(HI_K);
                 constexpr uint32_t HI_V_HI = uint32_t(HI_V >> 32), HI_V_LO = uint32_t(HI_V);
                 auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
-                // A cursor walks the CTA's stream of K/V block slots: (item ordinal, block within the item).
-                struct Cur { uint32_t it, j, n0, n1; bool valid; };
-                auto cur_load = [&](Cur& c) {                       // c.it set: fetch the item's trip counts
-                    Work w;
-                    c.valid = fetch_work(bar(B_WKFULL), wring, c.it, w);
-                    c.n0 = w.n0; c.n1 = w.n1; c.j = 0;
-                };
-                auto cur_next = [&](Cur c) -> Cur {
-                    if (c.j + 1 < c.n1) { ++c.j; return c; }
-                    ++c.it;
-                    cur_load(c);
-                    return c;
-                };
                 auto acquire = [&]() -> uint32_t {                  // wait for the next tile of the load order
                     const uint32_t st = ring.stage;
-                    tr.ev(6, st);
                     mbar_wait<HOT_HINT>(bar(B_KVFULL + st), ring.phase);
-                    tr.ev(7, st);
                     ring.advance<NS>();
                     return st;
                 };
-                auto issue_qk = [&](uint32_t t, const Cur& c, uint32_t kstage) {  // S = Q_t K^T (waits until S has been drained)
-                    const uint32_t n = t ? c.n1 : c.n0;
-                    const uint32_t qi = 2 * c.it + t, qslot = qi % 3;
-                    if (c.j == 0) mbar_wait(bar(B_QFULL + qslot), (qi / 3) & 1);
-                    tr.ev(4, nqk);
+                auto issue_qk = [&](uint32_t t, uint32_t kstage) {  // S = Q_t K^T (waits until S has been drained)
                     if (nqk > 0) mbar_wait<HOT_HINT>(bar(B_SFREE), (nqk - 1) & 1);
-                    tr.ev(5, nqk);
                     ++nqk;
                     tc_fence_after();
-                    const uint32_t a_lo = HI_K_LO | ((sb + C::OFF_Q + qslot * C::TILE_BYTES) >> 4);
+                    const uint32_t a_lo = HI_K_LO | ((sb + C::OFF_Q + t * C::TILE_BYTES) >> 4);
                     const uint32_t b_lo = HI_K_LO | ((sb + C::OFF_KV + kstage * C::TILE_BYTES) >> 4);
                     const uint32_t d = tmem + C::COL_S;
 #pragma unroll
@@ -455,25 +401,19 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         mma_ss(d, mk(HI_K_HI, a_lo + off), mk(HI_K_HI, b_lo + off), IDESC_QK, kk > 0);
                     }
                     mma_commit(bar(B_SFULL + t));
-                    if (c.j == n - 1) mma_commit(bar(B_QEMPTY + qslot));   // last Q K^T of the item for this tile
                 };
-                auto issue_pv = [&](uint32_t t, const Cur& c, uint32_t vstage) {   // O_t (+)= P_t V
+                auto issue_pv = [&](uint32_t t, uint32_t vstage, bool first, bool last) {   // O_t (+)= P_t V
                     uint32_t& gpv = t ? gpv1 : gpv0;
-                    const uint32_t n = t ? c.n1 : c.n0;
-                    const bool first = c.j == 0, last = c.j == n - 1;
                     const uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
                     const uint32_t a = tmem + (t ? C::COL_P1 : C::COL_P0);
                     const uint32_t d = tmem + (t ? C::COL_O1 : C::COL_O0);
-                    tr.ev(1 + 16 * t, gpv);
                     mbar_wait<HOT_HINT>(bar(B_PFULL + t), gpv & 1);
-                    if (first) mbar_wait(bar(B_OEMPTY + t), (c.it & 1) ^ 1);   // epilogue drained the previous O_t
-                    tr.ev(2 + 16 * t, gpv);
+                    if (first) mbar_wait(bar(B_OEMPTY + t), (it & 1) ^ 1);   // epilogue drained the previous O_t
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 6; ++kk)
                         mma_ts(d, a + kk * 8, mk(HI_V_HI, b_lo + kk * (2048 >> 4)), IDESC_PV, (!first || kk > 0) ? 1u : 0u);
                     mbar_wait<HOT_HINT>(bar(B_PFULLB + t), gpv & 1);
-                    tr.ev(3 + 16 * t, gpv);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 6; kk < 8; ++kk)
@@ -482,79 +422,83 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     mma_commit(bar(B_PVDONE + t));
                     if (last) mma_commit(bar(B_OFULL + t));
                 };
-                // Slots i (PV), i+1 (QK of tile 1), i+2 (QK of tile 0) are in flight; in steady state the issue order is
-                //     PV_0(i)  QK_1(i+1)  PV_1(i)  QK_0(i+2)
-                // and the cursors cross work-item boundaries without draining the pipe.
-                Cur cC; cC.it = 0;
-                cur_load(cC);
-                if (cC.valid) {
-                    uint32_t kB = 0, kA = 0;
-                    {   // prologue: QK_0(s0) QK_1(s0) QK_0(s1)
-                        const uint32_t k0 = acquire();
-                        issue_qk(0, cC, k0);
-                        issue_qk(1, cC, k0);
-                        mma_commit(bar(B_KVFULL + NS + k0));
+                // Cross-item pipelining: tile 0's softmax warps would otherwise sit idle from their last P of an item until
+                // the whole prologue of the next one has gone through the pipe.  In the LAST iteration of an item, right
+                // after PV_0, the next item is fetched and its QK_0(0) issued (its K_0 is the next tile of the load order,
+                // its Q_0 was requested when the last QK_0 of this item released the buffer), so S_0(0) of the next item
+                // is ready about one MMA group after tile 0 finished.
+                bool have_next = false, next_ok = false, qk0_done = false;
+                uint32_t w_next = 0, k_pre = 0;
+                for (uint32_t w;; ++it) {
+                    if (have_next) { w = w_next; if (!next_ok) break; }
+                    else if (!get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it, w)) break;
+                    have_next = false;
+                    const Work wk = decode(p, w);
+                    const uint32_t n0 = wk.n0, n1 = wk.n1;          // n0 <= n1, n1 >= 1
+                    // ---- prologue: QK_0(0) QK_1(0) QK_0(1)
+                    uint32_t k_cur;
+                    if (qk0_done) {
+                        k_cur = k_pre;                              // K_0 acquired and QK_0(0) issued under the previous item
+                        qk0_done = false;
+                    } else {
+                        k_cur = acquire();                          // K_0
+                        mbar_wait(bar(B_QFULL + 0), it & 1);
+                        issue_qk(0, k_cur);
+                        if (n0 == 1) mma_commit(bar(B_QEMPTY + 0));
                     }
-                    Cur cB = cur_next(cC), cA = cB;
-                    if (cB.valid) {
-                        kB = acquire();
-                        if (cB.j < cB.n0) issue_qk(0, cB, kB);
-                        cA = cur_next(cB);
+                    mbar_wait(bar(B_QFULL + 1), it & 1);
+                    issue_qk(1, k_cur);
+                    if (n1 == 1) mma_commit(bar(B_QEMPTY + 1));
+                    mma_commit(bar(B_KVFULL + NS + k_cur));         // K_0 released
+                    uint32_t k_next = 0, k_next2 = 0;               // stages of K_{j+1}, K_{j+2}
+                    if (n1 > 1) {
+                        k_next = acquire();                         // K_1
+                        if (1 < n0) {
+                            issue_qk(0, k_next);
+                            if (n0 == 2) mma_commit(bar(B_QEMPTY + 0));
+                        }
                     }
-                    while (cC.valid) {
-                        const uint32_t v = acquire();               // V(s_i)
-                        if (cC.j < cC.n0) issue_pv(0, cC, v);
-                        if (cB.valid) {
-                            issue_qk(1, cB, kB);                    // last user of K(s_{i+1})
-                            mma_commit(bar(B_KVFULL + NS + kB));
+                    // ---- main loop
+                    for (uint32_t j = 0; j < n1; ++j) {
+                        const uint32_t v = acquire();               // V_j
+                        if (j < n0) issue_pv(0, v, j == 0, j == n0 - 1);
+                        if (j == n1 - 1 && p.cross_item) {          // last block: start the next item's tile 0
+                            next_ok = get_work(p, bar(B_WKFULL), bar(B_WKEMPTY), work_ring, it + 1, w_next);
+                            have_next = true;
+                            if (next_ok) {
+                                const Work wn = decode(p, w_next);
+                                k_pre = acquire();                  // K_0 of the next item: next tile of the load order
+                                mbar_wait(bar(B_QFULL + 0), (it + 1) & 1);
+                                issue_qk(0, k_pre);
+                                if (wn.n0 == 1) mma_commit(bar(B_QEMPTY + 0));
+                                qk0_done = true;
+                            }
                         }
-                        issue_pv(1, cC, v);
-                        mma_commit(bar(B_KVFULL + NS + v));         // V(s_i) released
-                        if (cB.valid && cA.valid) {
-                            kA = acquire();                         // K(s_{i+2})
-                            if (cA.j < cA.n0) issue_qk(0, cA, kA);
+                        if (j + 1 < n1) {
+                            issue_qk(1, k_next);                    // QK_1(j+1): last user of K_{j+1}
+                            if (j + 1 == n1 - 1) mma_commit(bar(B_QEMPTY + 1));
+                            mma_commit(bar(B_KVFULL + NS + k_next));
                         }
-                        if (cC.j == cC.n1 - 1) mbar_arrive(bar(B_WKEMPTY + (cC.it & (WK_SLOTS - 1))));   // item fully issued
-                        cC = cB; cB = cA; kB = kA;
-                        if (cA.valid) cA = cur_next(cA);
+                        issue_pv(1, v, j == 0, j == n1 - 1);
+                        mma_commit(bar(B_KVFULL + NS + v));         // V_j released
+                        if (j + 2 < n1) {
+                            k_next2 = acquire();                    // K_{j+2}
+                            if (j + 2 < n0) {
+                                issue_qk(0, k_next2);
+                                if (j + 2 == n0 - 1) mma_commit(bar(B_QEMPTY + 0));
+                            }
+                        }
+                        k_next = k_next2;
                     }
                 }
             }
         } else if (warp == 13) {
-            // ================================================= scheduler + TMA producer
+            // ================================================= TMA producer
             if (elect_one()) {
-                Tracer<TRACE> tr(p.trace, 3, true);
                 Ring ring;
-                uint32_t published = 0;
-                bool stop_published = false;
-                uint32_t w_pending = atomicAdd(p.sched_counter, 1u);
-                auto publish = [&]() {                              // item `published` <- decode(w_pending); claim one more
-                    if (stop_published) return;
-                    const uint32_t slot = published & (WK_SLOTS - 1);
-                    mbar_wait(bar(B_WKEMPTY + slot), ((published / WK_SLOTS) & 1) ^ 1);
-                    const uint32_t w = w_pending;
-                    Work wk;
-                    if (w < p.num_tiles) {
-                        w_pending = atomicAdd(p.sched_counter, 1u);   // consumed one item later: its latency is hidden
-                        wk = decode(p, w);
-                    } else {
-                        wk.bh = wk.bkv = wk.row0 = wk.n0 = wk.n1 = wk.j0 = wk.dbh = wk.drow = 0;
-                        stop_published = true;
-                    }
-                    ring_write(wring, slot, wk);
-                    mbar_arrive(bar(B_WKFULL + slot));
-                    ++published;
-                };
-                struct Cur { uint32_t it, j, n1, bkv, j0, bh, row0, dbh, drow; bool valid; };
-                auto cur_load = [&](Cur& c) {                       // c.it < published
-                    const Work w = ring_read(wring, c.it & (WK_SLOTS - 1));
-                    c.j = 0; c.n1 = w.n1; c.bkv = w.bkv; c.j0 = w.j0; c.bh = w.bh; c.row0 = w.row0; c.dbh = w.dbh; c.drow = w.drow;
-                    c.valid = w.n1 != 0;
-                };
+                uint32_t it = 0;
                 auto load_kv = [&](const CUtensorMap* map, uint32_t j, uint32_t bkv) {
-                    tr.ev(8, ring.stage);
                     mbar_wait(bar(B_KVFULL + NS + ring.stage), ring.phase ^ 1);
-                    tr.ev(9, ring.stage);
                     const uint32_t full = bar(B_KVFULL + ring.stage);
                     const uint32_t dst = sb + C::OFF_KV + ring.stage * C::TILE_BYTES;
                     mbar_expect_tx(full, C::TILE_BYTES);
@@ -563,36 +507,31 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         tma_load_3d(dst + c * C::CHUNK_BYTES, map, full, c * 64, (int32_t)(j * 128), (int32_t)bkv);
                     ring.advance<NS>();
                 };
-                auto load_q = [&](const Cur& c, uint32_t t) {
-                    const uint32_t qi = 2 * c.it + t, qslot = qi % 3;
-                    mbar_wait(bar(B_QEMPTY + qslot), ((qi / 3) & 1) ^ 1);
-                    const uint32_t full = bar(B_QFULL + qslot);
-                    mbar_expect_tx(full, C::TILE_BYTES);
+                for (;; ++it) {
+                    uint32_t w;
+                    {   // claim and publish the next work item
+                        const uint32_t slot = it & 3;
+                        mbar_wait(bar(B_WKEMPTY + slot), ((it >> 2) & 1) ^ 1);
+                        w = atomicAdd(p.sched_counter, 1u);
+                        work_ring[slot] = w;
+                        mbar_arrive(bar(B_WKFULL + slot));
+                        if (w >= p.num_tiles) break;
+                    }
+                    const Work wk = decode(p, w);
+                    load_kv(tmK, wk.j0, wk.bkv);
+                    for (uint32_t t = 0; t < 2; ++t) {
+                        mbar_wait(bar(B_QEMPTY + t), (it & 1) ^ 1);
+                        const uint32_t full = bar(B_QFULL + t);
+                        mbar_expect_tx(full, C::TILE_BYTES);
 #pragma unroll
-                    for (int ch = 0; ch < C::CHUNKS; ++ch)
-                        tma_load_3d(sb + C::OFF_Q + qslot * C::TILE_BYTES + ch * C::CHUNK_BYTES, tmQ, full, ch * 64,
-                                    (int32_t)(c.row0 + t * c.drow), (int32_t)(c.bh + t * c.dbh));
-                };
-                auto load_k = [&](const Cur& c) {                   // K of slot c; an item's Q tiles ride with its first K
-                    if (c.j == 0) load_q(c, 0);
-                    load_kv(tmK, c.j0 + c.j, c.bkv);
-                    if (c.j == 0) load_q(c, 1);
-                };
-                auto advance = [&](Cur& c, bool leading) {
-                    if (++c.j < c.n1) return;
-                    ++c.it;
-                    if (leading) publish();                         // keep one item published beyond the leading cursor
-                    cur_load(c);
-                };
-                publish(); publish();
-                Cur kc; kc.it = 0; cur_load(kc);
-                Cur vc = kc;
-                if (kc.valid) {
-                    load_k(kc); advance(kc, true);
-                    if (kc.valid) { load_k(kc); advance(kc, true); }
-                    while (vc.valid) {                              // load order K0 K1 V0 K2 V1 K3 ... over the whole stream
-                        load_kv(tmV, vc.j0 + vc.j, vc.bkv); advance(vc, false);
-                        if (kc.valid) { load_k(kc); advance(kc, true); }
+                        for (int c = 0; c < C::CHUNKS; ++c)
+                            tma_load_3d(sb + C::OFF_Q + t * C::TILE_BYTES + c * C::CHUNK_BYTES, tmQ, full, c * 64,
+                                        (int32_t)(wk.row0 + t * wk.drow), (int32_t)(wk.bh + t * wk.dbh));
+                    }
+                    if (wk.n1 > 1) load_kv(tmK, wk.j0 + 1, wk.bkv);   // same order as the MMA thread acquires
+                    for (uint32_t j = 0; j < wk.n1; ++j) {
+                        load_kv(tmV, wk.j0 + j, wk.bkv);
+                        if (j + 2 < wk.n1) load_kv(tmK, wk.j0 + j + 2, wk.bkv);
                     }
                 }
             }
@@ -603,29 +542,22 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     if (warp == 14) tmem_dealloc<512>(tmem);
 }
 
-}  // namespace fwd100
+}  // namespace fwd100v4
 
-#define AULE_FWD100(NAME, DD, BF, EMU, TP, TR)                                                          \
+#define AULE_FWD100V4(NAME, DD, BF, EMU, TP, HINT)                                                        \
     extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
+                                                              const __grid_constant__ CUtensorMap tmO,   \
                                                               const aule_kp::FwdParams p) {              \
-        fwd100::fwd_body<DD, BF, EMU, TP, TR>(&tmQ, &tmK, &tmV, p);                                      \
+        fwd100v4::fwd_body<DD, BF, EMU, TP, HINT>(&tmQ, &tmK, &tmV, &tmO, p);                              \
     }
 
-#ifndef AULE_FWD_EMU4
-#define AULE_FWD_EMU4 1          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
+#ifndef AULE_FWD_TRUNC
+#define AULE_FWD_TRUNC true      // bf16 P packed by bias-compensated truncation (PRMT) instead of F2FP
 #endif
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, true, false)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, true, false)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false, false)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false, false)
-#ifdef AULE_TUNING_VARIANTS
-// bring-up / tuning builds only (make EXTRA_NVFLAGS=-DAULE_TUNING_VARIANTS): selected with aule_set_kernel_path(16 + v)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 1, true, true)       // pipeline tracer compiled in (tools/fwd_trace.py)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 2, true, false)      // 50 % polynomial exp2
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 0, true, false)      // MUFU only
-AULE_FWD100(aule_fwd_sm100_bf16_d64_e0, 64, true, 1, true, true)
-AULE_FWD100(aule_fwd_sm100_bf16_d64_e1, 64, true, 2, true, false)
-AULE_FWD100(aule_fwd_sm100_bf16_d64_e2, 64, true, 3, true, false)
+#ifndef AULE_FWD_HINT
+#define AULE_FWD_HINT 1000000u   // suspend hint (ns) of the waits on the softmax <-> MMA critical path
 #endif
+AULE_FWD100V4(aule_fwd4_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
+AULE_FWD100V4(aule_fwd4_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)

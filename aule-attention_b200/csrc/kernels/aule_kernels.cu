@@ -3,5 +3,8 @@
 // src/lib.zig:29-50, and of hipModuleLoadData in src/backends/hip.zig:133-160).
 #include "attn_simt.cu"
 #include "attn_fwd_sm100.cu"
+#ifdef AULE_TUNING_VARIANTS
+#include "attn_fwd_sm100_v4.cu"
+#endif
 #include "attn_bwd_sm100.cu"
 #include "attn_paged_sm100.cu"

@@ -32,13 +32,40 @@ struct FwdParams {
                               // 0: 256 rows of one q-head
     uint32_t units_per_run;   // (batch, kv-head) units whose work items are scheduled together (L2 residency of K/V)
     uint32_t* sched_counter;  // zero-initialised per launch: next unclaimed work item (dynamic persistent scheduler)
-    int32_t cross_item;       // 1: the first Q K^T of the next work item is issued under the current item's last block
+    int32_t cross_item;       // v4 only: the first Q K^T of the next work item is issued under the current item's last block
+    unsigned long long* trace; // bring-up: CTA 0 records (tag << 48 | clock64) events here (4 x 4096 entries) or nullptr
 };
 
-// v4 layout: Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
-// tile | row statistics | mbarriers.  TMEM: one shared S buffer, P0, P1, O0, O1.
+// v5 layout: Q ring (3 tiles) | K/V ring (NS x [128 keys][D], K and V tiles interleaved, continuous across work
+// items) | row statistics | work descriptors (8 x 32 B) | mbarriers.  TMEM: one shared S buffer, P0, P1, O0, O1.
 template <int D>
 struct FwdCfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
+    static constexpr int NS = (D == 128) ? 4 : 8;               // K/V ring stages
+    static constexpr int NQ = 3;                                // Q ring slots: tile x of item k -> slot (2k + x) % 3
+    static constexpr int CHUNKS = D / 64;                       // 128-byte swizzle chunks per row
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;          // [128 rows][128 B]
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_Q = 0;
+    static constexpr uint32_t OFF_KV = OFF_Q + NQ * TILE_BYTES;
+    static constexpr uint32_t OFF_STAT = OFF_KV + NS * TILE_BYTES; // float l[2][128], m[2][128]
+    static constexpr uint32_t OFF_WORK = OFF_STAT + 4 * 128 * 4;   // 8 work descriptors x 32 B
+    static constexpr uint32_t OFF_BAR = OFF_WORK + 8 * 32;
+    static constexpr int NBAR = 39 + 2 * NS;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+    // TMEM columns (512 allocated)
+    static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 192, COL_O0 = 256, COL_O1 = 256 + D;
+    // register budget per thread after setmaxnreg (512 threads x 128 at launch = 64 K registers):
+    // 2 softmax warpgroups x 184 + epilogue warpgroup x 64 + issuer/producer warpgroup x 80 = 512 x 128
+    static constexpr int REGS_SOFTMAX = 184, REGS_EPILOGUE = 64, REGS_OTHER = 80;
+};
+
+// v4 layout (attn_fwd_sm100_v4.cu, tuning builds only): Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
+// tile | row statistics | mbarriers.  TMEM: one shared S buffer, P0, P1, O0, O1.
+template <int D>
+struct FwdCfg4 {
     static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
     static constexpr int NS = (D == 128) ? 4 : 8;               // K/V ring stages
     static constexpr int CHUNKS = D / 64;                       // 128-byte swizzle chunks per row

@@ -7,7 +7,7 @@
 #include <stdint.h>
 
 #ifndef AULE_WATCHDOG
-#define AULE_WATCHDOG 1          // bound every mbarrier spin (traps instead of hanging the GPU)
+#define AULE_WATCHDOG 0          // 1 (bring-up): bound every mbarrier spin, print and trap instead of hanging the GPU
 #endif
 
 namespace sm100 {

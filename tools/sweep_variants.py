@@ -17,7 +17,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 paths = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 16, 17, 18]
 g = torch.Generator(device="cuda").manual_seed(42)
-B, Hq, Hkv, S, D = (4, 32, 32, 2048, 64) if os.environ.get("AULE_SWEEP_CFG") == "B" else (8, 32, 8, 4096, 128)
+B, Hq, Hkv, S, D = {"B": (4, 32, 32, 2048, 64), "D8": (1, 4, 4, 32768, 128), "C": (8, 32, 8, 4096, 128)}[os.environ.get("AULE_SWEEP_CFG", "C")]
 q = torch.randn(B, Hq, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
 k = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
 v = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
