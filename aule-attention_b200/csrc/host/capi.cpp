@@ -21,9 +21,11 @@ struct TensorSlot {
 };
 TensorSlot g_tensors[kMaxTensors];
 
-char g_error[512];                           // lib.zig:20
-size_t g_error_len = 0;
-char g_name_buf[300];
+// lib.zig:20 keeps one static buffer; here one per calling thread (ctypes releases the GIL, so two Python threads can fail
+// at the same time): the pointer aule_get_error() returns stays valid until the next failing call ON THAT THREAD.
+thread_local char g_error[512];
+thread_local size_t g_error_len = 0;
+thread_local char g_name_buf[300];
 
 void set_error(const char* fmt, ...) {       // lib.zig:23-25
     va_list ap;
@@ -319,7 +321,7 @@ int32_t aule_synchronize(int32_t device) {
 }
 uint64_t aule_launch_count(void) { return g_engine.launch_count(); }
 const char* aule_last_kernel(void) {
-    snprintf(g_name_buf, sizeof(g_name_buf), "%s", g_engine.last_kernel());
+    snprintf(g_name_buf, sizeof(g_name_buf), "%s", g_engine.last_kernel().c_str());
     return g_name_buf;
 }
 int32_t aule_set_kernel_path(int32_t path) {

@@ -50,6 +50,15 @@ namespace aule {
     X(cuEventRecord, cuEventRecord)                                                              \
     X(cuEventSynchronize, cuEventSynchronize)                                                    \
     X(cuEventDestroy, cuEventDestroy_v2)                                                         \
+    X(cuEventElapsedTime, cuEventElapsedTime)                                                    \
+    X(cuEventQuery, cuEventQuery)                                                                \
+    X(cuMemHostAlloc, cuMemHostAlloc)                                                            \
+    X(cuMemFreeHost, cuMemFreeHost)                                                              \
+    X(cuPointerGetAttribute, cuPointerGetAttribute)                                              \
+    X(cuMemcpyPeerAsync, cuMemcpyPeerAsync)                                                      \
+    X(cuMemcpyDtoDAsync, cuMemcpyDtoDAsync_v2)                                                   \
+    X(cuDeviceCanAccessPeer, cuDeviceCanAccessPeer)                                              \
+    X(cuCtxEnablePeerAccess, cuCtxEnablePeerAccess)                                              \
     X(cuTensorMapEncodeTiled, cuTensorMapEncodeTiled)
 
 struct CudaDriver {

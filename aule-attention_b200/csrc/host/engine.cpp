@@ -132,8 +132,8 @@ std::string Engine::load_device(int ordinal) {
     }
     // tuning builds only: optional symbols
     for (int dd = 0; dd < 2; ++dd) {
-        for (int v = 0; v < 3; ++v) {
-            const std::string nm = std::string("aule_fwd_sm100_bf16_d") + (dd ? "128" : "64") + "_e" + char('0' + v);
+        for (int v = 0; v < 16; ++v) {
+            const std::string nm = std::string("aule_fwd_sm100_bf16_d") + (dd ? "128" : "64") + "_e" + std::to_string(v);
             if (drv_.cuModuleGetFunction(&d.fwd_sm100_var[dd][v], d.mod, nm.c_str()) != CUDA_SUCCESS) { d.fwd_sm100_var[dd][v] = nullptr; continue; }
             drv_.cuFuncSetAttribute(d.fwd_sm100_var[dd][v], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                     dd ? (int)FwdCfg<128>::SMEM_BYTES : (int)FwdCfg<64>::SMEM_BYTES);
@@ -156,7 +156,14 @@ std::string Engine::load_device(int ordinal) {
                                               (int)aule_kp::PagedCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem paged d128)");
     }
     if (e.empty()) e = get(&d.smoke, "aule_smoke_multiply");
-    if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, 1024 * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
+    if (e.empty()) e = check(drv_.cuMemAlloc(&d.sched, Device::kSchedSlots * sizeof(uint32_t)), "cuMemAlloc(scheduler counters)");
+    for (uint32_t i = 0; i < Device::kSchedSlots && e.empty(); ++i)
+        e = check(drv_.cuEventCreate(&d.sched_ev[i], CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+    for (uint32_t i = 0; i < Device::kMaxChunks && e.empty(); ++i) {
+        e = check(drv_.cuEventCreate(&d.ev_in[i], CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        if (e.empty()) e = check(drv_.cuEventCreate(&d.ev_c[i], CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+    }
+    for (int i = 0; i < 4 && e.empty(); ++i) e = check(drv_.cuEventCreate(&d.bounce_ev[i], CU_EVENT_DISABLE_TIMING), "cuEventCreate");
     if (e.empty()) {
         // The backward's Delta workspace comes from the stream-ordered pool (cuMemAllocAsync). With the default
         // release threshold (0) the pool hands its memory back to the OS at every synchronisation and the next
@@ -175,6 +182,8 @@ std::string Engine::load_device(int ordinal) {
         drv_.cuDevicePrimaryCtxRelease(d.dev);
         return e;
     }
+    if ((int)devices_.size() >= kMaxDevices) return "too many devices";
+    d.index = (int)devices_.size();
     devices_.push_back(d);
     return "";
 }
@@ -187,6 +196,11 @@ void Engine::shutdown() {
         for (int i = 0; i < 9; ++i)
             if (d.stage[i]) drv_.cuMemFree(d.stage[i]);
         if (d.sched) drv_.cuMemFree(d.sched);
+        for (CUevent ev : d.sched_ev) if (ev) drv_.cuEventDestroy(ev);
+        for (CUevent ev : d.ev_in) if (ev) drv_.cuEventDestroy(ev);
+        for (CUevent ev : d.ev_c) if (ev) drv_.cuEventDestroy(ev);
+        for (CUevent ev : d.bounce_ev) if (ev) drv_.cuEventDestroy(ev);
+        for (int i = 0; i < 4; ++i) if (d.bounce[i]) drv_.cuMemFreeHost(d.bounce[i]);
         if (d.s_in) drv_.cuStreamDestroy(d.s_in);
         if (d.s_compute) drv_.cuStreamDestroy(d.s_compute);
         if (d.s_out) drv_.cuStreamDestroy(d.s_out);
@@ -225,6 +239,7 @@ std::string Engine::launch(Device& d, CUfunction fn, const char* name, unsigned 
     std::string e = check(drv_.cuLaunchKernel(fn, gx, gy, gz, bx, 1, 1, smem, stream, params, nullptr), name);
     if (e.empty()) {
         ++launches_;
+        std::lock_guard<std::mutex> g(name_mu_);
         last_kernel_ = name;
     }
     (void)d;
@@ -290,10 +305,21 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         p.scale_log2 = scale * 1.4426950408889634f;
         p.causal = causal ? 1 : 0;
         p.window = causal ? window : -1;
-        // one zeroed work counter per launch, from a ring (a slot is reused 1024 launches later)
-        const CUdeviceptr counter = d.sched + 4ull * (d.sched_next++ & 1023u);
+        // one zeroed work counter per launch, from a ring; the slot's previous user (any stream) must have finished
+        std::lock_guard<std::mutex> launch_guard(launch_mu_[d.index]);
+        const uint32_t slot = d.sched_next++ % Device::kSchedSlots;
+        if (d.sched_ev_live[slot] && !(e = check(drv_.cuEventSynchronize(d.sched_ev[slot]), "cuEventSynchronize(scheduler slot)")).empty()) return e;
+        const CUdeviceptr counter = d.sched + 4ull * slot;
         if (!(e = check(drv_.cuMemsetD32Async(counter, 0, 1, stream), "cuMemsetD32Async(scheduler counter)")).empty()) return e;
         p.sched_counter = (uint32_t*)counter;
+        auto launch_fwd = [&](CUfunction f, const char* nm, unsigned g_, unsigned smem_, void** prm) -> std::string {
+            std::string le = launch(d, f, nm, g_, 1, 1, 512, smem_, stream, prm);
+            if (le.empty()) {
+                le = check(drv_.cuEventRecord(d.sched_ev[slot], stream), "cuEventRecord(scheduler slot)");
+                d.sched_ev_live[slot] = le.empty();
+            }
+            return le;
+        };
         p.cross_item = cross_item_enabled_ ? 1 : 0;
         p.trace = (unsigned long long*)trace_;
         const bool d128 = s.D == 128;
@@ -303,19 +329,19 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
             if (dtype != kBF16 || !d.fwd4_sm100[d128 ? 1 : 0]) return "the v4 forward kernel is only present in tuning builds (bf16)";
             void* params4[] = {&tmQ, &tmK, &tmV, &tmO, &p};
             snprintf(name, sizeof(name), "aule_fwd4_sm100_bf16_d%u", s.D);
-            return launch(d, d.fwd4_sm100[d128 ? 1 : 0], name, grid, 1, 1, 512,
-                          d128 ? aule_kp::FwdCfg4<128>::SMEM_BYTES : aule_kp::FwdCfg4<64>::SMEM_BYTES, stream, params4);
+            return launch_fwd(d.fwd4_sm100[d128 ? 1 : 0], name, grid,
+                              d128 ? aule_kp::FwdCfg4<128>::SMEM_BYTES : aule_kp::FwdCfg4<64>::SMEM_BYTES, params4);
         }
         const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
         void* params[] = {&tmQ, &tmK, &tmV, &p};
         snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
         CUfunction fn = d.fwd_sm100[dtype][d128 ? 1 : 0];
-        if (path_ >= kVariantBase && path_ < kVariantBase + 3) {
+        if (path_ >= kVariantBase && path_ < kVariantBase + 16) {
             if (dtype != kBF16 || !d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase]) return "forward tuning variants are only present in tuning builds (bf16)";
             fn = d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase];
             snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d%u_e%d", s.D, path_ - kVariantBase);
         }
-        return launch(d, fn, name, grid, 1, 1, 512, smem, stream, params);
+        return launch_fwd(fn, name, grid, smem, params);
     }
     SimtParams p;
     memset(&p, 0, sizeof(p));
@@ -442,6 +468,27 @@ std::string Engine::ensure_stage(Device& d, int slot, size_t bytes) {
     return e;
 }
 
+bool Engine::host_pinned(const void* p) const {
+    // CU_MEMORYTYPE_HOST for page-locked (cuMemHostAlloc / cudaHostRegister / torch pin_memory) allocations; the query
+    // fails with CUDA_ERROR_INVALID_VALUE for ordinary pageable memory.
+    unsigned int mt = 0;
+    return drv_.cuPointerGetAttribute(&mt, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(uintptr_t)p) == CUDA_SUCCESS &&
+           mt == CU_MEMORYTYPE_HOST;
+}
+
+std::string Engine::ensure_bounce(Device& d, int slot, size_t bytes) {
+    if (d.bounce_cap[slot] >= bytes) return "";
+    if (d.bounce[slot]) {
+        drv_.cuCtxSynchronize();
+        drv_.cuMemFreeHost(d.bounce[slot]);
+        d.bounce[slot] = nullptr;
+        d.bounce_cap[slot] = 0;
+    }
+    std::string e = check(drv_.cuMemHostAlloc(&d.bounce[slot], bytes, 0), "cuMemHostAlloc(bounce buffer)");
+    if (e.empty()) d.bounce_cap[slot] = bytes;
+    return e;
+}
+
 std::string Engine::forward_host(int dev, const void* q, const void* k, const void* v, void* o, float* lse,
                                  const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window,
                                  int* stage_code) {
@@ -454,6 +501,7 @@ std::string Engine::forward_host(int dev, const void* q, const void* k, const vo
     if (!e.empty()) return e;
     if (!q || !k || !v || !o) return "null host pointer";
     Device& d = *dp;
+    std::lock_guard<std::mutex> host_guard(host_mu_[d.index]);   // staging buffers and the three streams are per device
     CtxGuard g(drv_, d.ctx);
     const size_t es = dtype_size(dtype);
     const uint32_t group = s.Hq / s.Hkv;
@@ -469,51 +517,101 @@ std::string Engine::forward_host(int dev, const void* q, const void* k, const vo
     if (lse && !(e = ensure_stage(d, 4, lse_unit * units)).empty()) return e;
 
     // Chunk over units so that copy-in of chunk c+1, the kernel of chunk c and copy-out of
-    // chunk c-1 overlap (three streams, events between them).
+    // chunk c-1 overlap (three streams, persistent events between them).
     // 8 chunks measured best on config C (9.04 ms per call; 16: 9.20, 32: 10.06 -- per-copy overheads outgrow the
     // shorter fill/drain of the pipeline); AULE_HOST_CHUNKS overrides (tuning hook).
     uint32_t want_chunks = 8;
     if (const char* ov = getenv("AULE_HOST_CHUNKS")) { const long v_ = atol(ov); if (v_ > 0) want_chunks = (uint32_t)v_; }
+    want_chunks = std::min<uint32_t>(want_chunks, Device::kMaxChunks);
     const uint32_t nchunks = std::min<uint32_t>(units, want_chunks);
     const uint32_t per = (units + nchunks - 1) / nchunks;
-    std::vector<CUevent> ev_in(nchunks, nullptr), ev_c(nchunks, nullptr);
-    auto cleanup = [&]() {
-        for (CUevent x : ev_in) if (x) drv_.cuEventDestroy(x);
-        for (CUevent x : ev_c) if (x) drv_.cuEventDestroy(x);
+
+    // Pageable callers (every NumPy caller of the legacy ABI): the DMA engines cannot read pageable memory, and the
+    // driver's own fallback is a synchronous staged copy.  Stage through the library's pinned bounce buffers instead,
+    // double-buffered per chunk: the CPU fills / drains one buffer while the copy engine works on the other.
+    const bool in_pinned = host_pinned(q) && host_pinned(k) && host_pinned(v);
+    const bool out_pinned = host_pinned(o) && (!lse || host_pinned(lse));
+    const size_t in_chunk = (size_t)per * (q_unit + 2 * kv_unit), out_chunk = (size_t)per * (q_unit + (lse ? lse_unit : 0));
+    if (!in_pinned)
+        for (int b = 0; b < 2; ++b)
+            if (!(e = ensure_bounce(d, b, in_chunk)).empty()) return e;
+    if (!out_pinned)
+        for (int b = 2; b < 4; ++b)
+            if (!(e = ensure_bounce(d, b, out_chunk)).empty()) return e;
+    bool bounce_busy[4] = {false, false, false, false};
+
+    struct Pending { bool live = false; uint32_t u0 = 0, nu = 0; int buf = 0; } pend;   // download waiting in a bounce buffer
+    auto drain = [&](Pending& pd) -> std::string {            // bounce buffer -> caller's pageable output
+        if (!pd.live) return "";
+        std::string de = check(drv_.cuEventSynchronize(d.bounce_ev[pd.buf]), "download");
+        if (!de.empty()) return de;
+        const char* src = (const char*)d.bounce[pd.buf];
+        memcpy((char*)o + pd.u0 * q_unit, src, pd.nu * q_unit);
+        if (lse) memcpy((char*)lse + pd.u0 * lse_unit, src + pd.nu * q_unit, pd.nu * lse_unit);
+        bounce_busy[pd.buf] = false;
+        pd.live = false;
+        return "";
     };
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        drv_.cuEventCreate(&ev_in[c], CU_EVENT_DISABLE_TIMING);
-        drv_.cuEventCreate(&ev_c[c], CU_EVENT_DISABLE_TIMING);
-    }
+
     int code = 0;
     for (uint32_t c = 0; c < nchunks && e.empty(); ++c) {
         const uint32_t u0 = c * per;
         if (u0 >= units) break;
         const uint32_t nu = std::min(per, units - u0);
         code = -3;
-        e = check(drv_.cuMemcpyHtoDAsync(d.stage[0] + u0 * q_unit, (const char*)q + u0 * q_unit, nu * q_unit, d.s_in), "upload Q");
-        if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[1] + u0 * kv_unit, (const char*)k + u0 * kv_unit, nu * kv_unit, d.s_in), "upload K");
-        if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[2] + u0 * kv_unit, (const char*)v + u0 * kv_unit, nu * kv_unit, d.s_in), "upload V");
-        if (e.empty()) e = check(drv_.cuEventRecord(ev_in[c], d.s_in), "cuEventRecord");
-        if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_compute, ev_in[c], 0), "cuStreamWaitEvent");
+        if (in_pinned) {
+            e = check(drv_.cuMemcpyHtoDAsync(d.stage[0] + u0 * q_unit, (const char*)q + u0 * q_unit, nu * q_unit, d.s_in), "upload Q");
+            if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[1] + u0 * kv_unit, (const char*)k + u0 * kv_unit, nu * kv_unit, d.s_in), "upload K");
+            if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[2] + u0 * kv_unit, (const char*)v + u0 * kv_unit, nu * kv_unit, d.s_in), "upload V");
+        } else {
+            const int b = (int)(c & 1);
+            if (bounce_busy[b]) e = check(drv_.cuEventSynchronize(d.bounce_ev[b]), "upload");   // its previous DMA has finished
+            if (e.empty()) {
+                char* bb = (char*)d.bounce[b];
+                memcpy(bb, (const char*)q + u0 * q_unit, nu * q_unit);
+                memcpy(bb + nu * q_unit, (const char*)k + u0 * kv_unit, nu * kv_unit);
+                memcpy(bb + nu * (q_unit + kv_unit), (const char*)v + u0 * kv_unit, nu * kv_unit);
+                e = check(drv_.cuMemcpyHtoDAsync(d.stage[0] + u0 * q_unit, bb, nu * q_unit, d.s_in), "upload Q");
+                if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[1] + u0 * kv_unit, bb + nu * q_unit, nu * kv_unit, d.s_in), "upload K");
+                if (e.empty()) e = check(drv_.cuMemcpyHtoDAsync(d.stage[2] + u0 * kv_unit, bb + nu * (q_unit + kv_unit), nu * kv_unit, d.s_in), "upload V");
+                if (e.empty()) e = check(drv_.cuEventRecord(d.bounce_ev[b], d.s_in), "cuEventRecord");
+                bounce_busy[b] = true;
+            }
+        }
+        if (e.empty()) e = check(drv_.cuEventRecord(d.ev_in[c], d.s_in), "cuEventRecord");
+        if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_compute, d.ev_in[c], 0), "cuStreamWaitEvent");
         if (!e.empty()) break;
         code = -4;
         // A chunk of `nu` units is itself a [nu, group, S, D] / [nu, 1, S, D] attention problem.
         AttnShape cs{nu, group, 1, s.Sq, s.Sk, s.D};
         e = forward(dev, d.s_compute, d.stage[0] + u0 * q_unit, d.stage[1] + u0 * kv_unit, d.stage[2] + u0 * kv_unit,
                     d.stage[3] + u0 * q_unit, lse ? d.stage[4] + u0 * lse_unit : 0, cs, dtype, scale, causal, window);
-        if (e.empty()) e = check(drv_.cuEventRecord(ev_c[c], d.s_compute), "cuEventRecord");
-        if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_out, ev_c[c], 0), "cuStreamWaitEvent");
+        if (e.empty()) e = check(drv_.cuEventRecord(d.ev_c[c], d.s_compute), "cuEventRecord");
+        if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_out, d.ev_c[c], 0), "cuStreamWaitEvent");
         if (!e.empty()) break;
         code = -5;
-        e = check(drv_.cuMemcpyDtoHAsync((char*)o + u0 * q_unit, d.stage[3] + u0 * q_unit, nu * q_unit, d.s_out), "download O");
-        if (e.empty() && lse)
-            e = check(drv_.cuMemcpyDtoHAsync((char*)lse + u0 * lse_unit, d.stage[4] + u0 * lse_unit, nu * lse_unit, d.s_out), "download LSE");
+        if (out_pinned) {
+            e = check(drv_.cuMemcpyDtoHAsync((char*)o + u0 * q_unit, d.stage[3] + u0 * q_unit, nu * q_unit, d.s_out), "download O");
+            if (e.empty() && lse)
+                e = check(drv_.cuMemcpyDtoHAsync((char*)lse + u0 * lse_unit, d.stage[4] + u0 * lse_unit, nu * lse_unit, d.s_out), "download LSE");
+        } else {
+            const int b = 2 + (int)(c & 1);
+            Pending mine;
+            mine.live = true; mine.u0 = u0; mine.nu = nu; mine.buf = b;
+            if (bounce_busy[b]) e = "internal: download bounce buffer still busy";
+            char* bb = (char*)d.bounce[b];
+            if (e.empty()) e = check(drv_.cuMemcpyDtoHAsync(bb, d.stage[3] + u0 * q_unit, nu * q_unit, d.s_out), "download O");
+            if (e.empty() && lse) e = check(drv_.cuMemcpyDtoHAsync(bb + nu * q_unit, d.stage[4] + u0 * lse_unit, nu * lse_unit, d.s_out), "download LSE");
+            if (e.empty()) e = check(drv_.cuEventRecord(d.bounce_ev[b], d.s_out), "cuEventRecord");
+            bounce_busy[b] = true;
+            if (e.empty()) e = drain(pend);                    // the previous chunk's output, while this chunk computes
+            pend = mine;
+        }
     }
     if (e.empty()) { code = -4; e = check(drv_.cuStreamSynchronize(d.s_compute), "attention kernel"); }
     if (e.empty()) { code = -5; e = check(drv_.cuStreamSynchronize(d.s_out), "download"); }
+    if (e.empty()) e = drain(pend);
     if (!e.empty()) { drv_.cuStreamSynchronize(d.s_in); drv_.cuStreamSynchronize(d.s_compute); drv_.cuStreamSynchronize(d.s_out); }
-    cleanup();
     *stage_code = e.empty() ? 0 : code;
     return e;
 }
@@ -529,6 +627,7 @@ std::string Engine::backward_host(int dev, const void* q, const void* k, const v
     std::string e = validate(s, dtype);
     if (!e.empty()) return e;
     Device& d = *dp;
+    std::lock_guard<std::mutex> host_guard(host_mu_[d.index]);
     CtxGuard g(drv_, d.ctx);
     const size_t es = dtype_size(dtype);
     const size_t qb = (size_t)s.B * s.Hq * s.Sq * s.D * es, kb = (size_t)s.B * s.Hkv * s.Sk * s.D * es;
@@ -561,6 +660,7 @@ std::string Engine::smoke_multiply(int dev, const float* in, float* out, uint32_
     Device* dp = by_ordinal(dev);
     if (!dp) return "invalid device index";
     Device& d = *dp;
+    std::lock_guard<std::mutex> host_guard(host_mu_[d.index]);
     CtxGuard g(drv_, d.ctx);
     std::string e;
     if (!(e = ensure_stage(d, 0, (size_t)n * 4)).empty()) return e;

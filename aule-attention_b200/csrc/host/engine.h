@@ -15,6 +15,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,7 +46,7 @@ struct Device {
     CUfunction bwd_dkv_simt[3] = {nullptr, nullptr, nullptr};
     CUfunction fwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     // present only in tuning builds (make EXTRA_NVFLAGS=-DAULE_TUNING_VARIANTS): bf16 variants [D==128][v] and the v4 kernel
-    CUfunction fwd_sm100_var[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    CUfunction fwd_sm100_var[2][16] = {};
     CUfunction fwd4_sm100[2] = {nullptr, nullptr};
     CUfunction bwd_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [dtype][D==128]
     CUfunction bwd_dkvt_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // transposed dK/dV kernel (v4)
@@ -56,9 +58,22 @@ struct Device {
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;
-    // per-launch work counters of the forward kernel's dynamic scheduler (ring of 1024 x u32, zeroed per launch)
+    int index = -1;                  // position in Engine::devices_ (selects the per-device mutexes)
+    // per-launch work counters of the forward kernel's dynamic scheduler: a ring of kSchedSlots x u32, each zeroed on the
+    // caller's stream before its launch.  A slot is handed out again only after the launch that last used it has
+    // completed (sched_ev, recorded on that launch's stream), whatever stream the next caller is on.
+    static constexpr uint32_t kSchedSlots = 256;
     CUdeviceptr sched = 0;
     uint32_t sched_next = 0;
+    CUevent sched_ev[kSchedSlots] = {};
+    bool sched_ev_live[kSchedSlots] = {};
+    // persistent events of the pipelined host-buffer entries (created once)
+    static constexpr uint32_t kMaxChunks = 32;
+    CUevent ev_in[kMaxChunks] = {}, ev_c[kMaxChunks] = {};
+    // pinned bounce buffers for pageable callers: [0,1] upload double buffer, [2,3] download double buffer
+    void* bounce[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t bounce_cap[4] = {0, 0, 0, 0};
+    CUevent bounce_ev[4] = {};
     // grow-only staging buffers for host-pointer calls: q k v o lse do dq dk dv
     CUdeviceptr stage[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     size_t stage_cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -126,13 +141,15 @@ public:
         pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
-    uint64_t launch_count() const { return launches_; }
-    const char* last_kernel() const { return last_kernel_.c_str(); }
+    uint64_t launch_count() const { return launches_.load(); }
+    std::string last_kernel() { std::lock_guard<std::mutex> g(name_mu_); return last_kernel_; }
 
 private:
     std::string check(CUresult r, const char* what) const;
     std::string load_device(int ordinal);
     std::string ensure_stage(Device& d, int slot, size_t bytes);
+    std::string ensure_bounce(Device& d, int slot, size_t bytes);
+    bool host_pinned(const void* p) const;
     std::string launch(Device& d, CUfunction fn, const char* name, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
                        unsigned smem, CUstream stream, void** params);
     std::string make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D) const;
@@ -151,8 +168,13 @@ private:
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)
     uint64_t trace_ = 0;
-    uint64_t launches_ = 0;
+    std::atomic<uint64_t> launches_{0};
     std::string last_kernel_ = "none";
+    // Thread safety (ctypes releases the GIL during calls): the device-pointer entries only share the scheduler-counter
+    // ring (launch_mu_); the host-pointer entries share the staging buffers and the three internal streams and are
+    // serialised per device (host_mu_).
+    static constexpr int kMaxDevices = 64;
+    std::mutex launch_mu_[kMaxDevices], host_mu_[kMaxDevices], name_mu_;
 };
 
 // RAII: make a device's primary context current for the duration of a call.

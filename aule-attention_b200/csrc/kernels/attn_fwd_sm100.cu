@@ -161,7 +161,16 @@ struct Tracer {
     }
 };
 
-template <int D, bool BF16, int EMU4, bool TRUNC_PACK, bool TRACE>
+// VAR (tuning bits of the softmax loop; A/B results in profiles/r2_fwd_softmax_loop.md):
+//   1       wait for pv_done only before the third P chunk is stored (P[0:96] is held in registers meanwhile)   [shipped]
+//   2       publish P once per block (all four chunks, one wait::st)
+//   4       S is loaded in two halves, the first half's row maximum is computed under the second half's TMEM load
+//   65536   scalar FFMA instead of FFMA2 for x = s*scale - m
+//   131072  x = s*scale - m computed in a pass of its own (in place) before the exp2 loop instead of interleaved  [shipped]
+//   256     softmax-only microbenchmark (tools/softmax_only.py): no MMA / TMA / epilogue, no barriers;
+//           + 512 tile 0 only, + 1024 tile 1 half a block late; diagnostics that BREAK the result: 2048 no row maximum,
+//           4096 no P stores, 8192 no S loads, 16384 no scale/offset, 32768 no row sum
+template <int D, bool BF16, int EMUN, int EMUD, bool TRUNC_PACK, bool TRACE, int VAR>
 __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorMap* tmK, const CUtensorMap* tmV,
                                          const FwdParams& p) {
     using C = Cfg<D>;
@@ -215,6 +224,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     constexpr uint32_t IDESC_QK = instr_desc_f16(BF16, 128, 128, false);
     constexpr uint32_t IDESC_PV = instr_desc_f16(BF16, 128, D, true);
 
+    constexpr bool SO = (VAR & 256) != 0;   // softmax-only microbenchmark: no MMA / TMA / epilogue, no barriers (tools/softmax_only.py)
     if (warp < 8) {
         // ===================================================== softmax warps
         reg_inc<C::REGS_SOFTMAX>();
@@ -227,27 +237,69 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         Tracer<TRACE> tr(p.trace, 1 + t, (warp & 3) == 0 && lane == 0);
         uint32_t g = 0, it = 0;                                     // g: blocks processed so far by this tile
         Work wk;
-        for (; fetch_work(bar(B_WKFULL), wring, it, wk); ++it) {
-            mbar_arrive(bar(B_WKEMPTY + (it & (WK_SLOTS - 1))));    // descriptor copied to registers
+        auto WAIT = [&](uint32_t b, uint32_t parity) { if constexpr (!SO) mbar_wait<HOT_HINT>(b, parity); };
+        auto ARRIVE = [&](uint32_t b) { if constexpr (!SO) mbar_arrive(b); };
+        if constexpr (SO) {                                         // benign scores: S = 0 everywhere
+            uint32_t z[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_st32(tS + c * 32, z);
+            tmem_wait_st();
+            named_bar_sync(2, 256);
+        }
+        if constexpr ((VAR & 1024) != 0) {                          // anti-phase: tile 1 starts half a block late
+            if (t == 1) { const long long w0 = clock64(); while (clock64() - w0 < 1400) {} }
+        }
+        const long long so_t0 = SO ? clock64() : 0;
+        for (; SO ? (it < 1 && !((VAR & 512) && t == 1)) : fetch_work(bar(B_WKFULL), wring, it, wk); ++it) {
+            if constexpr (SO) { wk.bh = wk.bkv = wk.j0 = wk.dbh = wk.drow = 0; wk.row0 = 1u << 24; wk.n0 = wk.n1 = 400; }
+            ARRIVE(bar(B_WKEMPTY + (it & (WK_SLOTS - 1))));    // descriptor copied to registers
             const uint32_t n = t ? wk.n1 : wk.n0;
             const uint32_t trow0 = wk.row0 + t * wk.drow;
             const uint32_t grow = trow0 + r;                        // global query row
             float m_used = -INFINITY, l = 0.f;
             for (uint32_t j = 0; j < n; ++j, ++g) {
                 tr.ev(10, g);
-                mbar_wait<HOT_HINT>(bar(B_SFULL + t), g & 1);
+                WAIT(bar(B_SFULL + t), g & 1);
                 tr.ev(11, g);
                 tc_fence_after();
-                uint32_t s[4][32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
-                tmem_wait_ld();
-                tc_fence_before();
-                mbar_arrive(bar(B_SFREE));                          // S may be overwritten by the next Q K^T
-                tr.ev(12, g);
                 const uint32_t jg = wk.j0 + j;                      // global K/V block index
                 const bool win_edge = p.window > 0 && jg * 128 + (uint32_t)p.window < trow0 + 128;   // some key left of a row's window
-                const bool need_mask = (p.causal && jg * 128 + 127 > trow0) || ((jg + 1) * 128 > p.Sk) || win_edge;
+                const bool need_mask = !SO && ((p.causal && jg * 128 + 127 > trow0) || ((jg + 1) * 128 > p.Sk) || win_edge);
+                uint32_t s[4][32];
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                bool half_done = false;
+                if ((VAR & 4) && !need_mask) {                      // first half's maximum under the second half's TMEM load
+                    tmem_ld32(tS, s[0]);
+                    tmem_ld32(tS + 32, s[1]);
+                    tmem_wait_ld();
+                    tmem_ld32(tS + 64, s[2]);
+                    tmem_ld32(tS + 96, s[3]);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
+                            mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+                            mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+                            mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+                        }
+                    half_done = true;
+                } else if (!(VAR & 8192) || g == 0) {               // (diagnostic bit 8192: S stays in registers after block 0)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+                }
+                if (VAR & 8192) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(s[c][i]));   // keep the values opaque
+                }
+                tmem_wait_ld();
+                tc_fence_before();
+                ARRIVE(bar(B_SFREE));                               // S may be overwritten by the next Q K^T
+                tr.ev(12, g);
                 if (need_mask) {                                    // diagonal / ragged-tail / window-edge blocks only: kept rolled (I-cache)
                     const uint32_t lim = p.causal ? min(grow, p.Sk - 1) : p.Sk - 1;   // last visible key
                     const int32_t thr = (int32_t)lim - (int32_t)(jg * 128);           // local columns > thr are masked (a suffix)
@@ -266,9 +318,10 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         }
                     }
                 }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 2 && half_done) continue;
+                    if ((VAR & 2048) && g > 0) continue;            // diagnostic (softmax-only runs): no row maximum
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
@@ -276,6 +329,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
                         mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
                     }
+                }
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
                 // Lazy rescale: adopt the new maximum only when it grew by more than 2^8 in the
                 // exp2 domain; otherwise P stays <= 256, harmless in bf16/fp16 and fp32 sums.
@@ -286,7 +340,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     l *= alpha;
                     if (grow_max) m_used = m_new;
                     if (j > 0) {
-                        mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);   // PV_t(j-1) complete: O_t is stable
+                        WAIT(bar(B_PVDONE + t), (g - 1) & 1);              // PV_t(j-1) complete: O_t is stable
                         pv_waited = true;
                         tc_fence_after();
 #pragma unroll 1
@@ -305,57 +359,112 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 // +log2(1+2^-9) so that the truncated values are unbiased, and l is corrected by the same factor.
                 const float neg_ms = ((m_used == -INFINITY) ? 0.f : -m_used * p.scale_log2) + ((BF16 && TRUNC_PACK) ? 0.0028150156f : 0.f);
                 // P = exp2(s*scale_log2 - m*scale_log2), two values per instruction (f32x2). EMU4 of every 4
-                // pairs may take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2.
+                // pairs may take a polynomial path (FMA/ALU pipes) instead of MUFU.EX2 (EMUN of every EMUD pairs).
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-                uint32_t pk[2][16];
+                if constexpr ((VAR & 131072) != 0) {                // scale/offset pass of its own, in place
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+                            s[c][2 * i] = __float_as_uint(x.x); s[c][2 * i + 1] = __float_as_uint(x.y);
+                        }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(s[c][i]));
+                }
+                uint32_t pk[4][16];
+                constexpr bool NOST = (VAR & 4096) != 0;            // diagnostic (softmax-only runs): P is not stored
+                auto ST16 = [&](uint32_t a, const uint32_t* r) {
+                    if constexpr (NOST) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) asm volatile("" ::"r"(r[i]));
+                    } else {
+                        tmem_st16(a, r);
+                    }
+                };
+                auto WAIT_ST = [&]() { if constexpr (!NOST) tmem_wait_st(); };
+                auto wait_pv = [&]() {                              // P_t is still being read by PV_t of the previous block until pv_done
+                    tr.ev(14, g);
+                    if (g > 0 && !pv_waited) WAIT(bar(B_PVDONE + t), (g - 1) & 1);
+                    tr.ev(15, g);
+                    tc_fence_after();
+                };
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+                        float2 x;
+                        if constexpr ((VAR & 16384) || (VAR & 131072)) {          // (131072: x was computed in a pass of its own)
+                            x = make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]));
+                        } else if constexpr ((VAR & 65536) != 0) {                 // scalar FFMA instead of the packed form
+                            x.x = fmaf(__uint_as_float(s[c][2 * i]), p.scale_log2, neg_ms);
+                            x.y = fmaf(__uint_as_float(s[c][2 * i + 1]), p.scale_log2, neg_ms);
+                        } else {
+                            x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+                        }
                         float2 e;
-                        if ((i & 3) < EMU4) {
+                        if ((i % EMUD) < EMUN) {
                             e = ex2_emu2(x);
                         } else {
                             e.x = ex2(x.x);
                             e.y = ex2(x.y);
                         }
-                        if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e);
-                        pk[c & 1][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
+                        if (!(VAR & 32768)) { if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e); }
+                        pk[c][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
                     }
-                    if (c == 1) {
-                        // P_t is still being read by PV_t of the previous block until pv_done: the first
-                        // two chunks are computed under that MMA and stored once it has finished.
-                        tr.ev(14, g);
-                        if (g > 0 && !pv_waited) mbar_wait<HOT_HINT>(bar(B_PVDONE + t), (g - 1) & 1);
-                        tr.ev(15, g);
-                        tc_fence_after();
-                        tmem_st16(tP, pk[0]);
-                        tmem_st16(tP + 16, pk[1]);
-                    } else if (c == 2) {
-                        tmem_st16(tP + 32, pk[0]);                   // keys 0..95 ready: PV k-steps 0..5 may start
-                        tmem_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(bar(B_PFULL + t));
-                        tr.ev(16, g);
-                    } else if (c == 3) {
-                        tmem_st16(tP + 48, pk[1]);
-                        tmem_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(bar(B_PFULLB + t));
-                        tr.ev(17, g);
+                    if constexpr (VAR & 2) {                        // one publish per block
+                        if (c == 3) {
+                            wait_pv();
+                            ST16(tP, pk[0]); ST16(tP + 16, pk[1]); ST16(tP + 32, pk[2]); ST16(tP + 48, pk[3]);
+                            WAIT_ST();
+                            tc_fence_before();
+                            ARRIVE(bar(B_PFULL + t));
+                            ARRIVE(bar(B_PFULLB + t));
+                            tr.ev(17, g);
+                        }
+                    } else {
+                        if (c == 1 && !(VAR & 1)) {
+                            // the first two chunks are computed under PV_t of the previous block and stored once it has finished
+                            wait_pv();
+                            ST16(tP, pk[0]);
+                            ST16(tP + 16, pk[1]);
+                        } else if (c == 2) {
+                            if (VAR & 1) {
+                                wait_pv();
+                                ST16(tP, pk[0]);
+                                ST16(tP + 16, pk[1]);
+                            }
+                            ST16(tP + 32, pk[2]);               // keys 0..95 ready: PV k-steps 0..5 may start
+                            WAIT_ST();
+                            tc_fence_before();
+                            ARRIVE(bar(B_PFULL + t));
+                            tr.ev(16, g);
+                        } else if (c == 3) {
+                            ST16(tP + 48, pk[3]);
+                            WAIT_ST();
+                            tc_fence_before();
+                            ARRIVE(bar(B_PFULLB + t));
+                            tr.ev(17, g);
+                        }
                     }
                 }
                 const float2 acc = __fadd2_rn(acc0, acc1);
                 l += acc.x + acc.y;
             }
             // hand the row statistics to the epilogue warps; a row that saw no visible key reports l = 0
-            mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
+            if constexpr (!SO) mbar_wait(bar(B_STEMPTY + t), (it & 1) ^ 1);
             sStat[t * 128 + r] = (m_used == -INFINITY) ? 0.f : ((BF16 && TRUNC_PACK) ? l * (1.f / 1.001953125f) : l);   // undo the 1+2^-9 bias carried by the exponents
             sStat[256 + t * 128 + r] = m_used;
-            mbar_arrive(bar(B_STFULL + t));
+            ARRIVE(bar(B_STFULL + t));
         }
+        if constexpr (SO) {
+            if (blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && p.trace) p.trace[t] = (unsigned long long)(clock64() - so_t0);
+        }
+    } else if (SO) {
+        reg_dec<C::REGS_EPILOGUE>();
     } else if (warp < 12) {
         // ===================================================== epilogue warps
         reg_dec<C::REGS_EPILOGUE>();
@@ -525,21 +634,28 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             if (elect_one()) {
                 Tracer<TRACE> tr(p.trace, 3, true);
                 Ring ring;
+                // Work items are claimed just in time: the atomic for item k+1 is issued when the K cursor is two slots from
+                // the end of item k (its latency hides under those slots) and its result is published when the cursor
+                // crosses the boundary.  Claiming earlier (v5 first claimed 2-3 items ahead) turns the heaviest-first dynamic
+                // schedule into a static one when a CTA only gets a handful of items: config D/8, 3.5 items per CTA, ran
+                // 25 % slower with the CTAs up to 30 % out of balance.
                 uint32_t published = 0;
-                bool stop_published = false;
-                uint32_t w_pending = atomicAdd(p.sched_counter, 1u);
-                auto publish = [&]() {                              // item `published` <- decode(w_pending); claim one more
-                    if (stop_published) return;
+                uint32_t w_pending = 0;
+                bool requested = false;
+                auto request = [&]() {
+                    if (!requested) { w_pending = atomicAdd(p.sched_counter, 1u); requested = true; }
+                };
+                auto publish = [&]() {                              // item `published` <- decode(w_pending)
+                    request();
+                    requested = false;
                     const uint32_t slot = published & (WK_SLOTS - 1);
                     mbar_wait(bar(B_WKEMPTY + slot), ((published / WK_SLOTS) & 1) ^ 1);
                     const uint32_t w = w_pending;
                     Work wk;
                     if (w < p.num_tiles) {
-                        w_pending = atomicAdd(p.sched_counter, 1u);   // consumed one item later: its latency is hidden
                         wk = decode(p, w);
                     } else {
                         wk.bh = wk.bkv = wk.row0 = wk.n0 = wk.n1 = wk.j0 = wk.dbh = wk.drow = 0;
-                        stop_published = true;
                     }
                     ring_write(wring, slot, wk);
                     mbar_arrive(bar(B_WKFULL + slot));
@@ -579,12 +695,14 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     if (c.j == 0) load_q(c, 1);
                 };
                 auto advance = [&](Cur& c, bool leading) {
-                    if (++c.j < c.n1) return;
+                    ++c.j;
+                    if (leading && c.j + 2 >= c.n1) request();      // claim the next item two slots before this one ends
+                    if (c.j < c.n1) return;
                     ++c.it;
-                    if (leading) publish();                         // keep one item published beyond the leading cursor
+                    if (leading) publish();
                     cur_load(c);
                 };
-                publish(); publish();
+                publish();
                 Cur kc; kc.it = 0; cur_load(kc);
                 Cur vc = kc;
                 if (kc.valid) {
@@ -605,27 +723,42 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 
 }  // namespace fwd100
 
-#define AULE_FWD100(NAME, DD, BF, EMU, TP, TR)                                                          \
+#define AULE_FWD100(NAME, DD, BF, EMUN, EMUD, TP, TR, VAR)                                                         \
     extern "C" __global__ void __launch_bounds__(512, 1) NAME(const __grid_constant__ CUtensorMap tmQ,   \
                                                               const __grid_constant__ CUtensorMap tmK,   \
                                                               const __grid_constant__ CUtensorMap tmV,   \
                                                               const aule_kp::FwdParams p) {              \
-        fwd100::fwd_body<DD, BF, EMU, TP, TR>(&tmQ, &tmK, &tmV, p);                                      \
+        fwd100::fwd_body<DD, BF, EMUN, EMUD, TP, TR, VAR>(&tmQ, &tmK, &tmV, p);                                      \
     }
 
-#ifndef AULE_FWD_EMU4
-#define AULE_FWD_EMU4 1          // polynomial-exp2 pairs per 4 pairs in the shipped kernels
+#ifndef AULE_FWD_EMUN
+#define AULE_FWD_EMUN 1          // polynomial-exp2 pairs: EMUN of every EMUD pairs in the shipped kernels
+#define AULE_FWD_EMUD 4
 #endif
-AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, true, false)
-AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, true, false)
-AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMU4, false, false)
-AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMU4, false, false)
+#ifndef AULE_FWD_VAR
+#define AULE_FWD_VAR (1 + 131072)   // shipped softmax loop: late pv_done wait + scale/offset pass of its own (see VAR above)
+#endif
+AULE_FWD100(aule_fwd_sm100_bf16_d128, 128, true, AULE_FWD_EMUN, AULE_FWD_EMUD, true, false, AULE_FWD_VAR)
+AULE_FWD100(aule_fwd_sm100_bf16_d64, 64, true, AULE_FWD_EMUN, AULE_FWD_EMUD, true, false, AULE_FWD_VAR)
+AULE_FWD100(aule_fwd_sm100_f16_d128, 128, false, AULE_FWD_EMUN, AULE_FWD_EMUD, false, false, AULE_FWD_VAR)
+AULE_FWD100(aule_fwd_sm100_f16_d64, 64, false, AULE_FWD_EMUN, AULE_FWD_EMUD, false, false, AULE_FWD_VAR)
 #ifdef AULE_TUNING_VARIANTS
 // bring-up / tuning builds only (make EXTRA_NVFLAGS=-DAULE_TUNING_VARIANTS): selected with aule_set_kernel_path(16 + v)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e0, 128, true, 1, true, true)       // pipeline tracer compiled in (tools/fwd_trace.py)
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e1, 128, true, 2, true, false)      // 50 % polynomial exp2
-AULE_FWD100(aule_fwd_sm100_bf16_d128_e2, 128, true, 0, true, false)      // MUFU only
-AULE_FWD100(aule_fwd_sm100_bf16_d64_e0, 64, true, 1, true, true)
-AULE_FWD100(aule_fwd_sm100_bf16_d64_e1, 64, true, 2, true, false)
-AULE_FWD100(aule_fwd_sm100_bf16_d64_e2, 64, true, 3, true, false)
+#define AULE_FWD_VARIANT(V, EMUN, EMUD, TR, VAR)                                                   \
+    AULE_FWD100(aule_fwd_sm100_bf16_d128_e##V, 128, true, EMUN, EMUD, true, TR, VAR)               \
+    AULE_FWD100(aule_fwd_sm100_bf16_d64_e##V, 64, true, EMUN, EMUD, true, TR, VAR)
+AULE_FWD_VARIANT(0, 1, 4, true, AULE_FWD_VAR)  // pipeline tracer compiled in (tools/fwd_trace.py)
+AULE_FWD_VARIANT(1, 1, 4, false, 1)            // interleaved scale/offset (round-2 first version)
+AULE_FWD_VARIANT(2, 1, 8, false, AULE_FWD_VAR) // 12.5 % polynomial exp2
+AULE_FWD_VARIANT(3, 0, 4, false, AULE_FWD_VAR) // MUFU only
+// softmax-only microbenchmarks (tools/softmax_only.py)
+AULE_FWD_VARIANT(4, 1, 4, false, 256 + AULE_FWD_VAR)
+AULE_FWD_VARIANT(5, 1, 4, false, 256 + AULE_FWD_VAR + 512)
+AULE_FWD_VARIANT(6, 1, 4, false, 256 + 1)
+AULE_FWD_VARIANT(7, 1, 4, false, 256 + 1 + 2048)
+AULE_FWD_VARIANT(8, 1, 4, false, 256 + 1 + 16384)
+AULE_FWD_VARIANT(9, 1, 4, false, 256 + 1 + 32768)
+AULE_FWD_VARIANT(10, 1, 4, false, 256 + 1 + 4096)
+AULE_FWD_VARIANT(11, 0, 4, false, 256 + 1)
+AULE_FWD_VARIANT(12, 1, 4, false, 256 + 1 + 65536)
 #endif

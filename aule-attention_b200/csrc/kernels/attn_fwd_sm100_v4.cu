@@ -559,5 +559,5 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
 #ifndef AULE_FWD_HINT
 #define AULE_FWD_HINT 1000000u   // suspend hint (ns) of the waits on the softmax <-> MMA critical path
 #endif
-AULE_FWD100V4(aule_fwd4_sm100_bf16_d128, 128, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
-AULE_FWD100V4(aule_fwd4_sm100_bf16_d64, 64, true, AULE_FWD_EMU4, AULE_FWD_TRUNC, AULE_FWD_HINT)
+AULE_FWD100V4(aule_fwd4_sm100_bf16_d128, 128, true, 1, AULE_FWD_TRUNC, AULE_FWD_HINT)
+AULE_FWD100V4(aule_fwd4_sm100_bf16_d64, 64, true, 1, AULE_FWD_TRUNC, AULE_FWD_HINT)

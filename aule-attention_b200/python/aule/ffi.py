@@ -198,6 +198,10 @@ class Aule:
         return self._lib.aule_has_shader_variant(variant) == 1
 
     def clear_tensors(self) -> None:
+        """vulkan.py:1120-1130: frees every handle-table slot of the library (all instances)."""
+        for t in self._tensors:
+            t._handle = 0                                            # the slots are gone: never destroy them twice
+        self._tensors = []
         self._lib.aule_tensor_clear_all()
 
     # ---- tensors (vulkan.py:571-611)
@@ -210,7 +214,9 @@ class Aule:
         h = create(*[int(x) for x in shape])
         if h == 0:
             raise AuleError(f"Failed to create tensor: {last_error()}")
-        return GpuTensor(self, h, tuple(shape), dtype)
+        t = GpuTensor(self, h, tuple(shape), dtype)
+        self._tensors.append(t)     # close() / __exit__ release it (the reference forgets this append, vulkan.py:211)
+        return t
 
     def attention_gpu(self, Q, K, V, output, rot_cos=None, rot_sin=None, causal=False, window_size=-1) -> None:
         """vulkan.py:613-659 -> aule_attention_forward_gpu."""
