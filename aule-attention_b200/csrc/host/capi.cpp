@@ -208,9 +208,12 @@ int32_t aule_attention_forward_gpu(uint64_t qh, uint64_t kh, uint64_t vh, uint64
     if (!g_engine.ready()) return -1;
     TensorSlot *q = slot_of(qh), *k = slot_of(kh), *v = slot_of(vh), *o = slot_of(oh);
     if (!q || !k || !v || !o) return -1;
-    if (rot_cos != 0 || rot_sin != 0) {
-        set_error("Attention failed: fused RoPE is not part of the B200 hot path (pass rot_cos = rot_sin = 0)");
-        return -3;
+    // RoPE argument pairing of AttentionEngine.forward (attention_gpu.zig:406-424): both or neither
+    TensorSlot *rc = nullptr, *rs = nullptr;
+    if ((rot_cos != 0) != (rot_sin != 0)) { set_error("Attention failed: rot_cos and rot_sin must be given together"); return -3; }
+    if (rot_cos != 0) {
+        rc = slot_of(rot_cos); rs = slot_of(rot_sin);
+        if (!rc || !rs) return -1;
     }
     // Shape rules of AttentionEngine.forward (attention_gpu.zig:372-400).
     if (k->shape[0] != q->shape[0] || k->shape[3] != q->shape[3]) { set_error("Attention failed: K batch/head_dim must match Q"); return -3; }
@@ -221,8 +224,17 @@ int32_t aule_attention_forward_gpu(uint64_t qh, uint64_t kh, uint64_t vh, uint64
     aule::AttnShape s{q->shape[0], q->shape[1], k->shape[1], q->shape[2], k->shape[2], q->shape[3]};
     const int dev = primary_device();
     aule::Device* d = g_engine.by_ordinal(dev);
-    std::string e = g_engine.forward(dev, d->s_compute, q->ptr, k->ptr, v->ptr, o->ptr, 0, s, aule::kF32, 0.f,
-                                     causal != 0, window_size);
+    std::string e;
+    if (rc) {
+        // The shader rotates interleaved pairs (2i, 2i+1) of Q and K by the angle of their row index, tables
+        // [.., seq, head_dim/2] (attention_f32.comp:98-111, tests/test_rope_unit.py:46-47): convention 1 of the RoPE kernel.
+        const uint32_t half = s.D / 2;
+        if (half == 0 || rc->count != rs->count || rc->count % half != 0) { set_error("Attention failed: rot_cos / rot_sin must hold [seq, head_dim/2] values"); return -3; }
+        e = g_engine.forward_rope(dev, d->s_compute, q->ptr, k->ptr, v->ptr, o->ptr, 0, rc->ptr, rs->ptr, rc->count / half, 1, s,
+                                  aule::kF32, 0.f, causal != 0, window_size);
+    } else {
+        e = g_engine.forward(dev, d->s_compute, q->ptr, k->ptr, v->ptr, o->ptr, 0, s, aule::kF32, 0.f, causal != 0, window_size);
+    }
     if (e.empty()) e = g_engine.synchronize(dev);       // the reference call is synchronous (attention_gpu.zig:456-469)
     if (!e.empty()) { set_error("Attention failed: %s", e.c_str()); return -3; }
     return 0;
@@ -288,11 +300,49 @@ int32_t aule_attention_forward_host(const void* q, const void* k, const void* v,
 }
 
 int32_t aule_rope_dptr(uint64_t x, uint64_t out, uint64_t cos, uint64_t sin, uint32_t B, uint32_t H, uint32_t S,
-                       uint32_t D, int32_t dtype, int32_t inverse, int32_t device, uint64_t cu_stream) {
+                       uint32_t D, uint32_t table_rows, int32_t interleaved, int32_t dtype, int32_t inverse, int32_t device,
+                       uint64_t cu_stream) {
     if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
-    std::string e = g_engine.rope(device, (CUstream)cu_stream, x, out, cos, sin, (uint64_t)B * H, S, D, dtype,
-                                  inverse ? -1.f : 1.f);
+    std::string e = g_engine.rope(device, (CUstream)cu_stream, x, out, (uint64_t)B * H, S, 0, 0, 0, 0, cos, sin, table_rows, D,
+                                  interleaved ? 1 : 0, dtype, inverse ? -1.f : 1.f);
     if (!e.empty()) { set_error("RoPE failed: %s", e.c_str()); return -4; }
+    return 0;
+}
+
+int32_t aule_attention_forward_rope_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse_or_0, uint64_t cos,
+                                         uint64_t sin, uint32_t table_rows, int32_t interleaved, uint32_t B, uint32_t Hq,
+                                         uint32_t Hkv, uint32_t Sq, uint32_t Sk, uint32_t D, int32_t dtype, float scale,
+                                         int32_t causal, int32_t window, int32_t device, uint64_t cu_stream) {
+    if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
+    aule::AttnShape s{B, Hq, Hkv, Sq, Sk, D};
+    std::string e = g_engine.forward_rope(device, (CUstream)cu_stream, q, k, v, o, lse_or_0, cos, sin, table_rows,
+                                          interleaved ? 1 : 0, s, dtype, scale, causal != 0, window);
+    if (!e.empty()) { set_error("Attention failed: %s", e.c_str()); return -4; }
+    return 0;
+}
+
+int32_t aule_attention_forward_spanning_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse_or_0, uint32_t B,
+                                             uint32_t Hq, uint32_t Hkv, uint32_t Sq, uint32_t Sk, uint32_t D, int32_t dtype,
+                                             float scale, int32_t causal, int32_t window, int32_t src_device,
+                                             uint64_t cu_stream, const int32_t* devices, int32_t num_devices, int32_t chunks,
+                                             float* timings_ms_or_null) {
+    if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
+    aule::AttnShape s{B, Hq, Hkv, Sq, Sk, D};
+    std::string e = g_engine.forward_spanning(src_device, (CUstream)cu_stream, q, k, v, o, lse_or_0, s, dtype, scale, causal != 0,
+                                              window, devices, num_devices, chunks, timings_ms_or_null);
+    if (!e.empty()) { set_error("Attention failed: %s", e.c_str()); return -4; }
+    return 0;
+}
+
+int32_t aule_attention_backward_host(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                     const float* lse, void* dq, void* dk, void* dv, uint32_t B, uint32_t Hq, uint32_t Hkv,
+                                     uint32_t Sq, uint32_t Sk, uint32_t D, int32_t dtype, float scale, int32_t causal,
+                                     int32_t device) {
+    if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
+    aule::AttnShape s{B, Hq, Hkv, Sq, Sk, D};
+    int code = 0;
+    std::string e = g_engine.backward_host(device, q, k, v, o, d_o, lse, dq, dk, dv, s, dtype, scale, causal != 0, &code);
+    if (!e.empty()) { set_error("Backward pass failed: %s", e.c_str()); return code ? code : -4; }
     return 0;
 }
 
@@ -338,6 +388,6 @@ int32_t aule_smoke_multiply(const float* in, float* out, uint32_t n) {
     if (!e.empty()) { set_error("Smoke kernel failed: %s", e.c_str()); return -4; }
     return 0;
 }
-const char* aule_version(void) { return "aule-b200 0.1.0 (abi 0.5.0+dptr1)"; }
+const char* aule_version(void) { return "aule-b200 0.2.0 (abi 0.5.0+dptr2)"; }
 
 }  // extern "C"

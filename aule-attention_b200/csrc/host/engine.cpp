@@ -38,6 +38,11 @@ CtxGuard::~CtxGuard() {
     }
 }
 
+bool Engine::log_enabled() {
+    static const bool on = [] { const char* v = getenv("AULE_LOG"); return v && *v && *v != '0'; }();
+    return on;
+}
+
 std::string Engine::check(CUresult r, const char* what) const {
     if (r == CUDA_SUCCESS) return "";
     return std::string(what) + ": " + drv_.error_string(r);
@@ -60,6 +65,15 @@ std::string Engine::init() {
         drv_.unload();
         return "no usable sm_100 device: " + why;
     }
+    // direct NVLink access between every pair of devices (spanning calls: cuMemcpyPeerAsync without a host bounce)
+    for (Device& a : devices_)
+        for (Device& b : devices_) {
+            if (a.index == b.index) continue;
+            int can = 0;
+            if (drv_.cuDeviceCanAccessPeer(&can, a.dev, b.dev) != CUDA_SUCCESS || !can) continue;
+            CtxGuard g(drv_, a.ctx);
+            drv_.cuCtxEnablePeerAccess(b.ctx, 0);       // CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED is fine (torch may have done it)
+        }
     ready_ = true;
     return "";
 }
@@ -177,6 +191,9 @@ std::string Engine::load_device(int ordinal) {
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_in, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_compute, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_out, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    if (e.empty()) e = check(drv_.cuStreamCreate(&d.s_aux, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+    if (e.empty()) e = check(drv_.cuEventCreate(&d.ev_fork, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+    if (e.empty()) e = check(drv_.cuEventCreate(&d.ev_join, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
     if (!e.empty()) {
         drv_.cuModuleUnload(d.mod);
         drv_.cuDevicePrimaryCtxRelease(d.dev);
@@ -204,6 +221,9 @@ void Engine::shutdown() {
         if (d.s_in) drv_.cuStreamDestroy(d.s_in);
         if (d.s_compute) drv_.cuStreamDestroy(d.s_compute);
         if (d.s_out) drv_.cuStreamDestroy(d.s_out);
+        if (d.s_aux) drv_.cuStreamDestroy(d.s_aux);
+        if (d.ev_fork) drv_.cuEventDestroy(d.ev_fork);
+        if (d.ev_join) drv_.cuEventDestroy(d.ev_join);
         if (d.mod) drv_.cuModuleUnload(d.mod);
     }
     for (Device& d : devices_) drv_.cuDevicePrimaryCtxRelease(d.dev);
@@ -275,15 +295,21 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
     if (!(scale > 0.f)) scale = 1.0f / sqrtf((float)s.D);   // triton_flash.py:394-395
     if (window == 0) window = -1;
 
-    // tensor-core path: 16-bit, D in {64,128}, full attention or a causal sliding window
-    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && (window < 0 || causal) &&
-                    path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0;
+    // Tensor-core path: 16-bit, any head_dim <= 128 that is a multiple of 8 (the TMA boxes zero-fill D up to 64 / 128, the
+    // way the reference pads to BLOCK_K = next_power_of_2(D), triton_flash.py:446), causal / full / sliding-window
+    // (one- or two-sided) masks.  Everything else (fp32, D % 8 != 0, unaligned pointers) runs the CUDA-core kernels;
+    // AULE_LOG=1 reports that choice on stderr.
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D % 8 == 0) && path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0;
+    if (!tc && log_enabled())
+        fprintf(stderr, "[aule] forward [%u,%u(%u),%u/%u,%u] %s: CUDA-core kernel (%s)\n", s.B, s.Hq, s.Hkv, s.Sq, s.Sk, s.D,
+                kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : (s.D % 8) ? "head_dim % 8 != 0" : "unaligned pointers");
     if (tc) {
+        const uint32_t DP = s.D <= 64 ? 64 : 128;             // kernel (padded) head_dim
         CUtensorMap tmQ, tmK, tmV, tmO;
         if (!(e = make_tmap(&tmQ, dtype, q, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
         if (!(e = make_tmap(&tmK, dtype, k, (uint64_t)s.B * s.Hkv, s.Sk, s.D)).empty()) return e;
         if (!(e = make_tmap(&tmV, dtype, v, (uint64_t)s.B * s.Hkv, s.Sk, s.D)).empty()) return e;
-        if (!(e = make_tmap(&tmO, dtype, o, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
+        if (fwd_v4_ && !(e = make_tmap(&tmO, dtype, o, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
         FwdParams p;
         p.lse = (float*)lse;
         p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk;
@@ -305,6 +331,11 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         p.scale_log2 = scale * 1.4426950408889634f;
         p.causal = causal ? 1 : 0;
         p.window = causal ? window : -1;
+        p.D_real = s.D;
+        // visibility i - win_left <= j <= i + win_right: causal keeps i-j < W (attention_f32.comp:176-178), the
+        // bidirectional window keeps |i-j| <= W/2 (:180-183)
+        p.win_right = causal ? 0u : (window > 0 ? (uint32_t)window / 2 : aule_kp::kWinInf);
+        p.win_left = window > 0 ? (causal ? (uint32_t)window - 1 : (uint32_t)window / 2) : aule_kp::kWinInf;
         // one zeroed work counter per launch, from a ring; the slot's previous user (any stream) must have finished
         std::lock_guard<std::mutex> launch_guard(launch_mu_[d.index]);
         const uint32_t slot = d.sched_next++ % Device::kSchedSlots;
@@ -322,24 +353,25 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         };
         p.cross_item = cross_item_enabled_ ? 1 : 0;
         p.trace = (unsigned long long*)trace_;
-        const bool d128 = s.D == 128;
+        const bool d128 = DP == 128;
         const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)d.sm_count);
         char name[64];
         if (fwd_v4_) {                     // A/B hook (tuning builds): the v4 kernel, TMA-stored output
-            if (dtype != kBF16 || !d.fwd4_sm100[d128 ? 1 : 0]) return "the v4 forward kernel is only present in tuning builds (bf16)";
+            if (dtype != kBF16 || !d.fwd4_sm100[d128 ? 1 : 0] || s.D != DP || (window > 0 && !causal))
+                return "the v4 forward kernel is only present in tuning builds (bf16, D in {64,128}, no bidirectional window)";
             void* params4[] = {&tmQ, &tmK, &tmV, &tmO, &p};
-            snprintf(name, sizeof(name), "aule_fwd4_sm100_bf16_d%u", s.D);
+            snprintf(name, sizeof(name), "aule_fwd4_sm100_bf16_d%u", DP);
             return launch_fwd(d.fwd4_sm100[d128 ? 1 : 0], name, grid,
                               d128 ? aule_kp::FwdCfg4<128>::SMEM_BYTES : aule_kp::FwdCfg4<64>::SMEM_BYTES, params4);
         }
         const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
         void* params[] = {&tmQ, &tmK, &tmV, &p};
-        snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+        snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], DP);
         CUfunction fn = d.fwd_sm100[dtype][d128 ? 1 : 0];
         if (path_ >= kVariantBase && path_ < kVariantBase + 16) {
             if (dtype != kBF16 || !d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase]) return "forward tuning variants are only present in tuning builds (bf16)";
             fn = d.fwd_sm100_var[d128 ? 1 : 0][path_ - kVariantBase];
-            snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d%u_e%d", s.D, path_ - kVariantBase);
+            snprintf(name, sizeof(name), "aule_fwd_sm100_bf16_d%u_e%d", DP, path_ - kVariantBase);
         }
         return launch_fwd(fn, name, grid, smem, params);
     }
@@ -388,6 +420,8 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             snprintf(name, sizeof(name), "aule_bwd_delta_%s", kDtypeSuffix[dtype]);
             e = launch(d, d.bwd_delta[dtype], name, (unsigned)((rows + 7) / 8), 1, 1, 256, 0, stream, params);
         }
+        std::lock_guard<std::mutex> launch_guard(launch_mu_[d.index]);   // s_aux and the fork / join events are per device
+        if (e.empty() && bwd_two_streams_) e = check(drv_.cuEventRecord(d.ev_fork, stream), "cuEventRecord");
         if (e.empty()) {
             CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
             e = make_tmap(&tmQ, dtype, q, (uint64_t)s.B * s.Hq, s.Sq, s.D);
@@ -423,11 +457,25 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
                 }
             }
             if (e.empty() && bwd_order_ != 1) {                 // (timing hook: 1 = dK/dV kernel only)
+                // The dQ kernel is independent of the dK/dV kernel (both only read q,k,v,dO,LSE,Delta): it runs on a second
+                // stream so that its CTAs fill the SMs the dK/dV kernel's last wave leaves idle (and vice versa) instead of
+                // waiting for that kernel's tail.  Fork after the Delta pre-pass, join before returning to the caller's stream.
+                const bool fork = bwd_order_ == 0 && !(bwd_serial_ & 1) && bwd_two_streams_;
+                CUstream sq = stream;
+                if (fork) {
+                    sq = d.s_aux;
+                    e = check(drv_.cuStreamWaitEvent(sq, d.ev_fork, 0), "cuStreamWaitEvent");
+                }
                 void* params[] = {&tmK, &tmV, &bp};
                 snprintf(name, sizeof(name), "aule_bwd_dq_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
-                e = launch(d, d.bwd_dq_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas_dq, 1, 1,
-                           (unsigned)aule_kp::BwdDqCfg<128>::THREADS,
-                           d128 ? aule_kp::BwdDqCfg<128>::SMEM_BYTES : aule_kp::BwdDqCfg<64>::SMEM_BYTES, stream, params);
+                if (e.empty())
+                    e = launch(d, d.bwd_dq_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas_dq, 1, 1,
+                               (unsigned)aule_kp::BwdDqCfg<128>::THREADS,
+                               d128 ? aule_kp::BwdDqCfg<128>::SMEM_BYTES : aule_kp::BwdDqCfg<64>::SMEM_BYTES, sq, params);
+                if (fork) {
+                    if (e.empty()) e = check(drv_.cuEventRecord(d.ev_join, sq), "cuEventRecord");
+                    if (e.empty()) e = check(drv_.cuStreamWaitEvent(stream, d.ev_join, 0), "cuStreamWaitEvent");
+                }
             }
         }
         drv_.cuMemFreeAsync(delta, stream);
@@ -673,22 +721,206 @@ std::string Engine::smoke_multiply(int dev, const float* in, float* out, uint32_
     return check(drv_.cuStreamSynchronize(d.s_compute), "smoke kernel");
 }
 
-std::string Engine::rope(int dev, CUstream stream, CUdeviceptr x, CUdeviceptr out, CUdeviceptr cos, CUdeviceptr sin,
-                         uint64_t bh, uint32_t S, uint32_t D, int32_t dtype, float sign) {
+std::string Engine::rope(int dev, CUstream stream, CUdeviceptr xq, CUdeviceptr oq, uint64_t bhq, uint32_t Sq, CUdeviceptr xk,
+                         CUdeviceptr ok, uint64_t bhk, uint32_t Sk, CUdeviceptr cos, CUdeviceptr sin, uint32_t table_rows,
+                         uint32_t D, int32_t mode, int32_t dtype, float sign) {
     if (!ready_) return "Library not initialized. Call aule_init() first.";
     Device* dp = by_ordinal(dev);
     if (!dp) return "invalid device index";
     if (dtype < 0 || dtype > 2) return "unsupported dtype (0=f32, 1=bf16, 2=f16)";
-    if (!x || !out || !cos || !sin) return "null device pointer";
-    if (D == 0 || (D & 1) || !S || !bh) return "RoPE needs an even head_dim and non-empty tensors";
+    if (!xq || !oq || !cos || !sin) return "null device pointer";
+    if (bhk && (!xk || !ok)) return "null device pointer";
+    if (D == 0 || (D & 1) || !Sq || !bhq) return "RoPE needs an even head_dim and non-empty tensors";
+    if (mode != 0 && mode != 1) return "RoPE convention must be 0 (half-split) or 1 (interleaved pairs)";
+    const uint32_t need = std::max(Sq, bhk ? Sk : 0u);
+    if (table_rows < need) {          // triton_flash.py:416-417 asserts the table shape; a short table would be read out of bounds
+        char buf[160];
+        snprintf(buf, sizeof(buf), "cos/sin tables have %u rows, the sequences need %u", table_rows, need);
+        return buf;
+    }
+    const size_t es = dtype_size(dtype);
+    const bool vec = (D % 8) == 0;
+    if (vec && (((xq | oq | xk | ok) & (es * 4 - 1)) || ((cos | sin) & 15))) return "RoPE tensors must be 16-byte aligned";
     Device& d = *dp;
     CtxGuard g(drv_, d.ctx);
-    uint64_t rows = bh * S;
-    void* params[] = {&x, &out, &cos, &sin, &rows, &S, &D, &sign};
+    aule_kp::RopeParams p;
+    p.xq = (const void*)xq; p.oq = (void*)oq; p.rows_q = bhq * Sq; p.Sq = Sq;
+    p.xk = (const void*)xk; p.ok = (void*)ok; p.rows_k = bhk ? bhk * Sk : 0; p.Sk = bhk ? Sk : 1;
+    p.cs = (const float*)cos; p.sn = (const float*)sin; p.D = D; p.mode = mode; p.sign = sign;
+    void* params[] = {&p};
     char name[32];
     snprintf(name, sizeof(name), "aule_rope_%s", kDtypeSuffix[dtype]);
-    const uint64_t work = rows * (D / 2);
-    return launch(d, d.rope[dtype], name, (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)d.sm_count * 16), 1, 1, 256, 0, stream, params);
+    const uint64_t work = (p.rows_q + p.rows_k) * (vec ? D / 8 : D / 2);
+    return launch(d, d.rope[dtype], name, (unsigned)std::min<uint64_t>((work + 255) / 256, (uint64_t)d.sm_count * 32), 1, 1, 256, 0, stream, params);
+}
+
+std::string Engine::forward_rope(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                                 CUdeviceptr lse, CUdeviceptr cos, CUdeviceptr sin, uint32_t table_rows, int32_t mode,
+                                 const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    Device* dp = by_ordinal(dev);
+    if (!dp) return "invalid device index";
+    std::string e = validate(s, dtype);
+    if (!e.empty()) return e;
+    if (!q || !k || !v || !o) return "null device pointer";
+    Device& d = *dp;
+    CtxGuard g(drv_, d.ctx);
+    // K has to be rotated once per key, not once per (query block, key) pair, so the rotation is a prologue: ONE launch reads
+    // Q and K once and writes the rotated copies once (stream-ordered workspace), then the fused kernel runs on them.
+    const size_t es = dtype_size(dtype);
+    const size_t qb = (size_t)s.B * s.Hq * s.Sq * s.D * es, kb = (size_t)s.B * s.Hkv * s.Sk * s.D * es;
+    CUdeviceptr ws = 0;
+    if (!(e = check(drv_.cuMemAllocAsync(&ws, qb + kb, stream), "cuMemAllocAsync(RoPE workspace)")).empty()) return e;
+    e = rope(dev, stream, q, ws, (uint64_t)s.B * s.Hq, s.Sq, k, ws + qb, (uint64_t)s.B * s.Hkv, s.Sk, cos, sin, table_rows, s.D,
+             mode, dtype, 1.f);
+    if (e.empty()) e = forward(dev, stream, ws, ws + qb, v, o, lse, s, dtype, scale, causal, window);
+    drv_.cuMemFreeAsync(ws, stream);
+    return e;
+}
+
+// A single call whose tensors live on ONE device, computed by several (SURVEY 8e "spanning call"): the (batch, kv-head)
+// units are split contiguously over `ndev` devices; every device other than the source receives its Q/K/V slabs over
+// NVLink (cuMemcpyPeerAsync), runs the fused kernel on them and returns its O (and LSE) slab; the source device computes
+// its own share in place.  Each peer works in `chunks` sub-ranges so that the copy-in of chunk c+1 and the copy-out of
+// chunk c-1 overlap the kernel of chunk c (three streams per device).  Asynchronous for the caller: `stream` of the source
+// device waits for the gathered result.  timings_ms (optional, makes the call synchronous):
+// [0] scatter, [1] kernel, [2] gather = max over devices of each phase's device-timed duration, [3] total on the source stream.
+std::string Engine::forward_spanning(int src_dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                                     CUdeviceptr lse, const AttnShape& s, int32_t dtype, float scale, bool causal,
+                                     int32_t window, const int32_t* devices, int32_t ndev, int32_t chunks, float* timings_ms) {
+    if (!ready_) return "Library not initialized. Call aule_init() first.";
+    std::string e = validate(s, dtype);
+    if (!e.empty()) return e;
+    if (!q || !k || !v || !o) return "null device pointer";
+    if (ndev < 1 || ndev > 64 || !devices) return "spanning call needs 1..64 devices";
+    Device* sp = by_ordinal(src_dev);
+    if (!sp) return "invalid source device index";
+    std::vector<Device*> devs;
+    for (int i = 0; i < ndev; ++i) {
+        Device* dp = by_ordinal(devices[i]);
+        if (!dp) return "invalid device index in the spanning set";
+        for (Device* x : devs) if (x == dp) return "duplicate device in the spanning set";
+        devs.push_back(dp);
+    }
+    if (std::find(devs.begin(), devs.end(), sp) == devs.end()) return "the source device must be part of the spanning set";
+    chunks = std::max(1, std::min<int32_t>(chunks, (int32_t)Device::kMaxChunks));
+    const size_t es = dtype_size(dtype);
+    const uint32_t group = s.Hq / s.Hkv, units = s.B * s.Hkv;
+    const size_t q_unit = (size_t)group * s.Sq * s.D * es, kv_unit = (size_t)s.Sk * s.D * es, lse_unit = (size_t)group * s.Sq * sizeof(float);
+    // contiguous unit ranges, as even as possible
+    std::vector<uint32_t> u0(ndev + 1, 0);
+    for (int i = 0; i < ndev; ++i) u0[i + 1] = u0[i] + units / ndev + ((uint32_t)i < units % ndev ? 1 : 0);
+    // lock every participating device's staging state in index order (no lock-order inversion between concurrent callers)
+    std::vector<Device*> order(devs);
+    std::sort(order.begin(), order.end(), [](Device* a, Device* b) { return a->index < b->index; });
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (Device* dp : order) locks.emplace_back(host_mu_[dp->index]);
+
+    struct Ev { CUevent ev[5] = {}; CUcontext ctx = nullptr; };   // in0, in1, k0, k1(=out0), out1 -- timing-enabled, per device
+    std::vector<Ev> evs(ndev);
+    auto cleanup = [&]() {
+        for (int i = 0; i < ndev; ++i) {
+            CtxGuard g(drv_, devs[i]->ctx);
+            for (CUevent x : evs[i].ev) if (x) drv_.cuEventDestroy(x);
+        }
+    };
+    CUevent ev_ready = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    {   // inputs are ready when the caller's stream reaches this point
+        CtxGuard g(drv_, sp->ctx);
+        e = check(drv_.cuEventCreate(&ev_ready, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        if (e.empty()) e = check(drv_.cuEventCreate(&ev_t0, CU_EVENT_DEFAULT), "cuEventCreate");
+        if (e.empty()) e = check(drv_.cuEventCreate(&ev_t1, CU_EVENT_DEFAULT), "cuEventCreate");
+        if (e.empty()) e = check(drv_.cuEventRecord(ev_t0, stream), "cuEventRecord");
+        if (e.empty()) e = check(drv_.cuEventRecord(ev_ready, stream), "cuEventRecord");
+    }
+    for (int i = 0; i < ndev && e.empty(); ++i) {
+        Device& d = *devs[i];
+        const uint32_t nu = u0[i + 1] - u0[i];
+        if (nu == 0) continue;
+        CtxGuard g(drv_, d.ctx);
+        for (int x = 0; x < 5 && e.empty(); ++x) e = check(drv_.cuEventCreate(&evs[i].ev[x], CU_EVENT_DEFAULT), "cuEventCreate");
+        if (!e.empty()) break;
+        AttnShape cs{nu, group, 1, s.Sq, s.Sk, s.D};
+        if (&d == sp) {                       // the source computes its own share in place, on its compute stream
+            e = check(drv_.cuStreamWaitEvent(d.s_compute, ev_ready, 0), "cuStreamWaitEvent");
+            if (e.empty()) e = check(drv_.cuEventRecord(evs[i].ev[2], d.s_compute), "cuEventRecord");
+            if (e.empty()) e = forward(d.ordinal, d.s_compute, q + u0[i] * q_unit, k + u0[i] * kv_unit, v + u0[i] * kv_unit,
+                                       o + u0[i] * q_unit, lse ? lse + u0[i] * lse_unit : 0, cs, dtype, scale, causal, window);
+            if (e.empty()) e = check(drv_.cuEventRecord(evs[i].ev[3], d.s_compute), "cuEventRecord");
+            continue;
+        }
+        if (!(e = ensure_stage(d, 0, q_unit * nu)).empty()) break;
+        if (!(e = ensure_stage(d, 1, kv_unit * nu)).empty()) break;
+        if (!(e = ensure_stage(d, 2, kv_unit * nu)).empty()) break;
+        if (!(e = ensure_stage(d, 3, q_unit * nu)).empty()) break;
+        if (lse && !(e = ensure_stage(d, 4, lse_unit * nu)).empty()) break;
+        e = check(drv_.cuStreamWaitEvent(d.s_in, ev_ready, 0), "cuStreamWaitEvent");
+        if (e.empty()) e = check(drv_.cuEventRecord(evs[i].ev[0], d.s_in), "cuEventRecord");
+        const uint32_t nch = std::min<uint32_t>((uint32_t)chunks, nu), per = (nu + nch - 1) / nch;
+        for (uint32_t c = 0; c < nch && e.empty(); ++c) {
+            const uint32_t a = c * per;
+            if (a >= nu) break;
+            const uint32_t n = std::min(per, nu - a), ga = u0[i] + a;      // local / global first unit of the chunk
+            e = check(drv_.cuMemcpyPeerAsync(d.stage[0] + a * q_unit, d.ctx, q + ga * q_unit, sp->ctx, n * q_unit, d.s_in), "scatter Q");
+            if (e.empty()) e = check(drv_.cuMemcpyPeerAsync(d.stage[1] + a * kv_unit, d.ctx, k + ga * kv_unit, sp->ctx, n * kv_unit, d.s_in), "scatter K");
+            if (e.empty()) e = check(drv_.cuMemcpyPeerAsync(d.stage[2] + a * kv_unit, d.ctx, v + ga * kv_unit, sp->ctx, n * kv_unit, d.s_in), "scatter V");
+            if (e.empty()) e = check(drv_.cuEventRecord(d.ev_in[c], d.s_in), "cuEventRecord");
+            if (e.empty() && c + 1 == nch) e = check(drv_.cuEventRecord(evs[i].ev[1], d.s_in), "cuEventRecord");
+            if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_compute, d.ev_in[c], 0), "cuStreamWaitEvent");
+            if (e.empty() && c == 0) e = check(drv_.cuEventRecord(evs[i].ev[2], d.s_compute), "cuEventRecord");
+            AttnShape ccs{n, group, 1, s.Sq, s.Sk, s.D};
+            if (e.empty()) e = forward(d.ordinal, d.s_compute, d.stage[0] + a * q_unit, d.stage[1] + a * kv_unit, d.stage[2] + a * kv_unit,
+                                       d.stage[3] + a * q_unit, lse ? d.stage[4] + a * lse_unit : 0, ccs, dtype, scale, causal, window);
+            if (e.empty()) e = check(drv_.cuEventRecord(d.ev_c[c], d.s_compute), "cuEventRecord");
+            if (e.empty() && c + 1 == nch) e = check(drv_.cuEventRecord(evs[i].ev[3], d.s_compute), "cuEventRecord");
+            if (e.empty()) e = check(drv_.cuStreamWaitEvent(d.s_out, d.ev_c[c], 0), "cuStreamWaitEvent");
+            if (e.empty()) e = check(drv_.cuMemcpyPeerAsync(o + ga * q_unit, sp->ctx, d.stage[3] + a * q_unit, d.ctx, n * q_unit, d.s_out), "gather O");
+            if (e.empty() && lse) e = check(drv_.cuMemcpyPeerAsync(lse + ga * lse_unit, sp->ctx, d.stage[4] + a * lse_unit, d.ctx, n * lse_unit, d.s_out), "gather LSE");
+        }
+        if (e.empty()) e = check(drv_.cuEventRecord(evs[i].ev[4], d.s_out), "cuEventRecord");
+    }
+    // the caller's stream continues when every device's result has landed on the source
+    if (e.empty()) {
+        CtxGuard g(drv_, sp->ctx);
+        for (int i = 0; i < ndev && e.empty(); ++i) {
+            if (u0[i + 1] == u0[i]) continue;
+            e = check(drv_.cuStreamWaitEvent(stream, devs[i] == sp ? evs[i].ev[3] : evs[i].ev[4], 0), "cuStreamWaitEvent");
+        }
+        if (e.empty()) e = check(drv_.cuEventRecord(ev_t1, stream), "cuEventRecord");
+    }
+    // The per-call events and the staging buffers are owned until the work has drained; timing needs it anyway.
+    {
+        CtxGuard g(drv_, sp->ctx);
+        CUresult r = drv_.cuEventSynchronize(ev_t1);
+        if (e.empty()) e = check(r, "spanning call");
+        for (Device* dp : devs) { CtxGuard g2(drv_, dp->ctx); drv_.cuStreamSynchronize(dp->s_in); drv_.cuStreamSynchronize(dp->s_compute); drv_.cuStreamSynchronize(dp->s_out); }
+    }
+    if (e.empty() && timings_ms) {
+        float sc = 0.f, kn = 0.f, ga = 0.f, tot = 0.f;
+        for (int i = 0; i < ndev; ++i) {
+            if (u0[i + 1] == u0[i]) continue;
+            CtxGuard g(drv_, devs[i]->ctx);
+            float ms = 0.f;
+            if (devs[i] != sp) {
+                if (drv_.cuEventElapsedTime(&ms, evs[i].ev[0], evs[i].ev[1]) == CUDA_SUCCESS) sc = std::max(sc, ms);
+                if (drv_.cuEventElapsedTime(&ms, evs[i].ev[3], evs[i].ev[4]) == CUDA_SUCCESS) ga = std::max(ga, ms);
+            }
+            if (drv_.cuEventElapsedTime(&ms, evs[i].ev[2], evs[i].ev[3]) == CUDA_SUCCESS) kn = std::max(kn, ms);
+        }
+        {
+            CtxGuard g(drv_, sp->ctx);
+            drv_.cuEventElapsedTime(&tot, ev_t0, ev_t1);
+        }
+        timings_ms[0] = sc; timings_ms[1] = kn; timings_ms[2] = ga; timings_ms[3] = tot;
+    }
+    cleanup();
+    {
+        CtxGuard g(drv_, sp->ctx);
+        if (ev_ready) drv_.cuEventDestroy(ev_ready);
+        if (ev_t0) drv_.cuEventDestroy(ev_t0);
+        if (ev_t1) drv_.cuEventDestroy(ev_t1);
+    }
+    return e;
 }
 
 std::string Engine::make_tmap_paged(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint32_t num_blocks,

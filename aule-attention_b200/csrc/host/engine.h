@@ -58,6 +58,9 @@ struct Device {
     CUfunction smoke = nullptr;
     // streams for the host-staged entry points
     CUstream s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+    // backward: the dQ kernel runs on s_aux beside the dK/dV kernel on the caller's stream (fork / join events)
+    CUstream s_aux = nullptr;
+    CUevent ev_fork = nullptr, ev_join = nullptr;
     int index = -1;                  // position in Engine::devices_ (selects the per-device mutexes)
     // per-launch work counters of the forward kernel's dynamic scheduler: a ring of kSchedSlots x u32, each zeroed on the
     // caller's stream before its launch.  A slot is handed out again only after the launch that last used it has
@@ -110,9 +113,19 @@ public:
                               const float* lse, void* dq, void* dk, void* dv, const AttnShape& s, int32_t dtype,
                               float scale, bool causal, int* stage_code);
     std::string smoke_multiply(int dev, const float* in, float* out, uint32_t n);
-    // out = RoPE(x) (half-split convention), x/out: [rows_total = B*H*S, D] of `dtype`, cos/sin: [S, D/2] fp32.
-    std::string rope(int dev, CUstream stream, CUdeviceptr x, CUdeviceptr out, CUdeviceptr cos, CUdeviceptr sin,
-                     uint64_t bh, uint32_t S, uint32_t D, int32_t dtype, float sign);
+    // RoPE of one or two tensors in one launch: x*/o*: [bh*, S*, D] of `dtype` (xk = 0: one tensor), cos/sin: [table_rows, D/2]
+    // fp32; mode 0 = half-split (triton_flash.py:680-703), 1 = interleaved pairs (attention_f32.comp:98-111); sign -1 = inverse.
+    std::string rope(int dev, CUstream stream, CUdeviceptr xq, CUdeviceptr oq, uint64_t bhq, uint32_t Sq, CUdeviceptr xk,
+                     CUdeviceptr ok, uint64_t bhk, uint32_t Sk, CUdeviceptr cos, CUdeviceptr sin, uint32_t table_rows,
+                     uint32_t D, int32_t mode, int32_t dtype, float sign);
+    // RoPE prologue (one launch over Q and K into a stream-ordered workspace) + fused attention.
+    std::string forward_rope(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                             CUdeviceptr lse, CUdeviceptr cos, CUdeviceptr sin, uint32_t table_rows, int32_t mode,
+                             const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window);
+    // One call spanning several devices (inputs resident on src_dev): NVLink scatter of Q/K/V slabs, kernels, gather of O/LSE.
+    std::string forward_spanning(int src_dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
+                                 CUdeviceptr lse, const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window,
+                                 const int32_t* devices, int32_t ndev, int32_t chunks, float* timings_ms);
 
     // Paged-KV decode (one query token per sequence; python/aule/triton_flash_amd.py:662-740): q/out [B,Hq,D],
     // k_cache/v_cache [num_blocks, block_size, Hkv, D], block_tables [B, max_blocks] i32, context_lens [B] i32.
@@ -136,11 +149,13 @@ public:
     //   bit 12     backward bring-up: the issuer waits for every MMA group (tools/bwd_trace.py serial)
     //   bit 13     backward: the v3 dK/dV kernel (P, dS staged through shared memory) instead of the transposed v4
     //   bit 14     forward: the v4 kernel (tuning builds only; an error otherwise)
+    //   bit 16     backward: dK/dV and dQ kernels back to back on the caller's stream (no second stream)
     //   bit 15     forward v4: no cross-item prefetch of the next work item's first Q K^T
     void set_kernel_path(int32_t p) {
-        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; path_ = p & 255;
+        pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; bwd_two_streams_ = !(p & 65536); path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
+    static bool log_enabled();     // AULE_LOG=1: report kernel-path choices (CUDA-core fallbacks) on stderr
     uint64_t launch_count() const { return launches_.load(); }
     std::string last_kernel() { std::lock_guard<std::mutex> g(name_mu_); return last_kernel_; }
 
@@ -165,6 +180,7 @@ private:
     bool cross_item_enabled_ = true;   // forward: next item's first Q K^T under the current item's last block (path bit 15 disables)
     int32_t bwd_order_ = 0;
     int32_t fwd_v4_ = 0;
+    bool bwd_two_streams_ = true;
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)
     uint64_t trace_ = 0;

@@ -95,24 +95,27 @@ __device__ __forceinline__ Work decode(const FwdParams& p, uint32_t w) {
     const uint32_t qrev = lw / per, rem = lw - qrev * per;
     const uint32_t unit = run * p.units_per_run + rem / ipu, hh = rem % ipu;
     const uint32_t b = unit / p.Hkv, hk = unit - b * p.Hkv;
-    const uint32_t ql = p.causal ? (p.num_q_super - 1 - qrev) : qrev; // heaviest first under causal
+    const bool heavy_last = p.win_right != aule_kp::kWinInf && p.win_left == aule_kp::kWinInf;   // plain causal: later rows are heavier
+    const uint32_t ql = heavy_last ? (p.num_q_super - 1 - qrev) : qrev;    // heaviest first
     t.bkv = unit;
-    t.j0 = 0;
+    // K/V block range of a 128-row tile starting at row r0: blocks holding a key in [r0 - win_left, r0 + 127 + win_right]
+    auto first_blk = [&](uint32_t r0) -> uint32_t { return r0 > p.win_left ? min((r0 - p.win_left) / 128, nkb - 1) : 0u; };
+    auto last_blk = [&](uint32_t r0) -> uint32_t {
+        return p.win_right == aule_kp::kWinInf ? nkb - 1 : min(nkb - 1, (r0 + 127 + p.win_right) / 128);
+    };
     if (p.pair_heads) {
         t.bh = b * p.Hq + hk * G + 2 * hh;
         t.row0 = ql * 128;
-        t.n0 = t.n1 = p.causal ? min(nkb, ql + 1) : nkb;
+        t.j0 = first_blk(t.row0);
+        t.n0 = t.n1 = max(last_blk(t.row0), t.j0) - t.j0 + 1;
         t.dbh = 1; t.drow = 0;
     } else {
         t.bh = b * p.Hq + hk * G + hh;
         t.row0 = ql * 256;
-        t.n0 = p.causal ? min(nkb, t.row0 / 128 + 1) : nkb;    // KV blocks tile 0 needs (diagonal included)
-        t.n1 = p.causal ? min(nkb, t.row0 / 128 + 2) : nkb;    // n0 <= n1 always
+        t.j0 = first_blk(t.row0);                               // common start: tile 0's first row is the leftmost
+        t.n0 = max(last_blk(t.row0), t.j0) - t.j0 + 1;          // tile 0: rows [row0, row0+128)
+        t.n1 = max(last_blk(t.row0 + 128), t.j0) - t.j0 + 1;    // tile 1: rows [row0+128, row0+256); n0 <= n1 always
         t.dbh = 0; t.drow = 128;
-    }
-    if (p.window > 0 && t.row0 + 1 > (uint32_t)p.window) {           // blocks entirely left of the window are skipped
-        t.j0 = min((t.row0 + 1 - (uint32_t)p.window) / 128, t.n0 - 1);  // common start (tile 0's first row is the leftmost)
-        t.n0 -= t.j0; t.n1 -= t.j0;
     }
     return t;
 }
@@ -265,8 +268,11 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 tr.ev(11, g);
                 tc_fence_after();
                 const uint32_t jg = wk.j0 + j;                      // global K/V block index
-                const bool win_edge = p.window > 0 && jg * 128 + (uint32_t)p.window < trow0 + 128;   // some key left of a row's window
-                const bool need_mask = !SO && ((p.causal && jg * 128 + 127 > trow0) || ((jg + 1) * 128 > p.Sk) || win_edge);
+                // a block needs masking when some row of the tile loses a column of it: right limit (causal diagonal / window),
+                // ragged key tail, left limit (window)
+                const bool need_mask = !SO && ((p.win_right != aule_kp::kWinInf && jg * 128 + 127 > trow0 + p.win_right) ||
+                                               ((jg + 1) * 128 > p.Sk) ||
+                                               (p.win_left != aule_kp::kWinInf && jg * 128 + p.win_left < trow0 + 127));
                 uint32_t s[4][32];
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 bool half_done = false;
@@ -301,9 +307,9 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 ARRIVE(bar(B_SFREE));                               // S may be overwritten by the next Q K^T
                 tr.ev(12, g);
                 if (need_mask) {                                    // diagonal / ragged-tail / window-edge blocks only: kept rolled (I-cache)
-                    const uint32_t lim = p.causal ? min(grow, p.Sk - 1) : p.Sk - 1;   // last visible key
+                    const uint32_t lim = p.win_right != aule_kp::kWinInf ? min(grow + p.win_right, p.Sk - 1) : p.Sk - 1;   // last visible key
                     const int32_t thr = (int32_t)lim - (int32_t)(jg * 128);           // local columns > thr are masked (a suffix)
-                    const int32_t lo = p.window > 0 ? (int32_t)grow - p.window + 1 - (int32_t)(jg * 128) : -1;   // local columns < lo are masked (a prefix)
+                    const int32_t lo = p.win_left != aule_kp::kWinInf ? (int32_t)grow - (int32_t)p.win_left - (int32_t)(jg * 128) : -1;   // local columns < lo are masked (a prefix)
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         if (thr >= c * 32 + 31 && lo <= c * 32) continue;
@@ -483,7 +489,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                 const uint32_t grow = wk.row0 + t * wk.drow + r;
                 const bool row_ok = grow < p.Sq;
                 const size_t orow = (size_t)(wk.bh + t * wk.dbh) * p.Sq + grow;
-                uint8_t* optr = reinterpret_cast<uint8_t*>(p.o) + orow * (size_t)(D * 2);
+                uint8_t* optr = reinterpret_cast<uint8_t*>(p.o) + orow * (size_t)(p.D_real * 2);
                 const float inv = (l > 0.f) ? 1.f / l : 0.f;        // rows without a visible key: O = 0, LSE = -inf
                 mbar_wait(bar(B_OFULL + t), it & 1);
                 tc_fence_after();
@@ -496,15 +502,23 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                         tc_fence_before();
                         mbar_arrive(bar(B_OEMPTY + t));
                     }
-                    // 32 fp32 -> 32 x 16-bit = 64 B of this row: two 256-bit stores (whole 32-byte sectors)
+                    // 32 fp32 -> 32 x 16-bit = 64 B of this row
                     uint32_t v[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) v[u] = pack2<BF16>(__uint_as_float(o[2 * u]) * inv, __uint_as_float(o[2 * u + 1]) * inv);
                     if (row_ok) {
-                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr + c * 64),
-                                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr + c * 64 + 32),
-                                     "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+                        if (p.D_real == (uint32_t)D) {              // two 256-bit stores (whole 32-byte sectors)
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr + c * 64),
+                                         "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr + c * 64 + 32),
+                                         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+                        } else {                                    // padded head_dim (D_real % 8 == 0): 128-bit pieces inside the row
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if ((uint32_t)(c * 32 + u * 8 + 8) <= p.D_real)
+                                    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(optr + c * 64 + u * 16),
+                                                 "r"(v[4 * u]), "r"(v[4 * u + 1]), "r"(v[4 * u + 2]), "r"(v[4 * u + 3]) : "memory");
+                        }
                     }
                 }
                 if (p.lse != nullptr && row_ok)

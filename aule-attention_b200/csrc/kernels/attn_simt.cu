@@ -111,14 +111,15 @@ __device__ __forceinline__ void frag_axpy(float (&a)[MAXG][4], float w, const fl
         }
 }
 
-// visible(i, j): key j contributes to query i.
+// visible(i, j): key j contributes to query i.  Sliding window (the Vulkan shader's convention, attention_f32.comp:173-183):
+// causal keeps 0 <= i-j < W, bidirectional keeps |i-j| <= W/2.
 __device__ __forceinline__ bool visible(uint32_t i, uint32_t j, uint32_t Sk, int causal, int window) {
     if (j >= Sk) return false;
     if (causal && j > i) return false;
     if (window > 0) {
         const int64_t d = (int64_t)i - (int64_t)j;
-        if (d >= window) return false;
-        if (!causal && -d >= window) return false;
+        if (causal) { if (d >= window) return false; }
+        else if (d > window / 2 || -d > window / 2) return false;
     }
     return true;
 }
@@ -322,27 +323,109 @@ extern "C" __global__ void aule_cvt_bf16_to_f32(const __nv_bfloat16* in, float* 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Rotary position embedding, half-split convention of the reference's Triton path
-// (python/aule/triton_flash.py:680-703 apply_rope_separate; rotate_half(x) = [-x2, x1]):
-//   out[d]       = x[d]       * cos[s,d] - x[d + D/2] * sin[s,d]
-//   out[d + D/2] = x[d + D/2] * cos[s,d] + x[d]       * sin[s,d]          d < D/2,  cos/sin: [S, D/2] fp32
+// Rotary position embedding of Q and K in ONE launch (the prologue of flash_attention_rope,
+// python/aule/triton_flash.py:561-603): each tensor is read once and written once.  Two pairing conventions:
+//   mode 0, half-split (Triton path, triton_flash.py:680-703 apply_rope_separate; rotate_half(x) = [-x2, x1]):
+//       out[d]       = x[d]       * cos[s,d] - x[d + D/2] * sin[s,d]
+//       out[d + D/2] = x[d + D/2] * cos[s,d] + x[d]       * sin[s,d]          d < D/2
+//   mode 1, interleaved pairs (Vulkan shader, shaders/attention_f32.comp:98-111; tests/test_rope_unit.py:76-85):
+//       out[2d]     = x[2d] * cos[s,d] - x[2d+1] * sin[s,d]
+//       out[2d + 1] = x[2d] * sin[s,d] + x[2d+1] * cos[s,d]
+// cos/sin: [table_rows, D/2] fp32, position s = row index inside its sequence (the host checks table_rows >= S).
 // `sign` = -1 applies the transpose (inverse rotation), which is what the backward pass needs.
-// Memory-bound elementwise pass (x read once, out written once); fp32 math.
+// Memory-bound; fp32 math; four pairs per thread (8- or 16-byte accesses) when D % 8 == 0, one pair otherwise.
 template <typename T>
-__device__ __forceinline__ void rope_body(const T* x, T* out, const float* cs, const float* sn, uint64_t rows,
-                                          uint32_t S, uint32_t D, float sign) {
-    const uint32_t half = D / 2;
-    const uint64_t total = rows * half;
+__device__ __forceinline__ void ld4f(const T* p, float (&f)[4]);
+template <>
+__device__ __forceinline__ void ld4f<float>(const float* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void ld4f<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void ld4f<__half>(const __half* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+template <typename T>
+__device__ __forceinline__ void st4f(T* p, const float (&f)[4]);
+template <>
+__device__ __forceinline__ void st4f<float>(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <>
+__device__ __forceinline__ void st4f<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a); v.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st4f<__half>(__half* p, const float (&f)[4]) {
+    __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a); v.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = v;
+}
+
+using aule_kp::RopeParams;
+
+template <typename T>
+__device__ __forceinline__ void rope_body(const RopeParams& p) {
+    const uint32_t half = p.D / 2;
+    const bool vec = (p.D % 8) == 0;
+    const uint32_t per_row = vec ? half / 4 : half;              // work items per row
+    const uint64_t nq = p.rows_q * per_row, total = nq + p.rows_k * per_row;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t row = i / half;
-        const uint32_t d = (uint32_t)(i - row * half);
+        const bool second = i >= nq;
+        const uint64_t w = second ? i - nq : i;
+        const T* x = reinterpret_cast<const T*>(second ? p.xk : p.xq);
+        T* out = reinterpret_cast<T*>(second ? p.ok : p.oq);
+        const uint32_t S = second ? p.Sk : p.Sq;
+        const uint64_t row = w / per_row;
+        const uint32_t u = (uint32_t)(w - row * per_row);
         const uint32_t s = (uint32_t)(row % S);
-        const float c = cs[(size_t)s * half + d], sv = sign * sn[(size_t)s * half + d];
-        const float x1 = Elem<T>::ld(x, row * D + d), x2 = Elem<T>::ld(x, row * D + d + half);
-        Elem<T>::st(out, row * D + d, x1 * c - x2 * sv);
-        Elem<T>::st(out, row * D + d + half, x2 * c + x1 * sv);
+        if (vec) {
+            const uint32_t d = 4 * u;                            // first of four pairs
+            float c[4], sv[4], a[4], b[4], ra[4], rb[4];
+            ld4f<float>(p.cs + (size_t)s * half + d, c);
+            ld4f<float>(p.sn + (size_t)s * half + d, sv);
+            if (p.mode == 0) {
+                ld4f<T>(x + row * p.D + d, a);
+                ld4f<T>(x + row * p.D + d + half, b);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ra[e] = a[e] * c[e] - b[e] * (p.sign * sv[e]);
+                    rb[e] = b[e] * c[e] + a[e] * (p.sign * sv[e]);
+                }
+                st4f<T>(out + row * p.D + d, ra);
+                st4f<T>(out + row * p.D + d + half, rb);
+            } else {
+                ld4f<T>(x + row * p.D + 2 * d, a);               // pairs (a0,a1) (a2,a3) (b0,b1) (b2,b3)
+                ld4f<T>(x + row * p.D + 2 * d + 4, b);
+                ra[0] = a[0] * c[0] - a[1] * (p.sign * sv[0]); ra[1] = a[0] * (p.sign * sv[0]) + a[1] * c[0];
+                ra[2] = a[2] * c[1] - a[3] * (p.sign * sv[1]); ra[3] = a[2] * (p.sign * sv[1]) + a[3] * c[1];
+                rb[0] = b[0] * c[2] - b[1] * (p.sign * sv[2]); rb[1] = b[0] * (p.sign * sv[2]) + b[1] * c[2];
+                rb[2] = b[2] * c[3] - b[3] * (p.sign * sv[3]); rb[3] = b[2] * (p.sign * sv[3]) + b[3] * c[3];
+                st4f<T>(out + row * p.D + 2 * d, ra);
+                st4f<T>(out + row * p.D + 2 * d + 4, rb);
+            }
+        } else {
+            const uint32_t d = u;
+            const float c = p.cs[(size_t)s * half + d], sv = p.sign * p.sn[(size_t)s * half + d];
+            const uint64_t i1 = p.mode == 0 ? row * p.D + d : row * p.D + 2 * d, i2 = p.mode == 0 ? i1 + half : i1 + 1;
+            const float x1 = Elem<T>::ld(x, i1), x2 = Elem<T>::ld(x, i2);
+            Elem<T>::st(out, i1, x1 * c - x2 * sv);
+            Elem<T>::st(out, i2, x2 * c + x1 * sv);
+        }
     }
 }
-extern "C" __global__ void aule_rope_f32(const float* x, float* out, const float* cs, const float* sn, uint64_t rows, uint32_t S, uint32_t D, float sign) { rope_body(x, out, cs, sn, rows, S, D, sign); }
-extern "C" __global__ void aule_rope_bf16(const __nv_bfloat16* x, __nv_bfloat16* out, const float* cs, const float* sn, uint64_t rows, uint32_t S, uint32_t D, float sign) { rope_body(x, out, cs, sn, rows, S, D, sign); }
-extern "C" __global__ void aule_rope_f16(const __half* x, __half* out, const float* cs, const float* sn, uint64_t rows, uint32_t S, uint32_t D, float sign) { rope_body(x, out, cs, sn, rows, S, D, sign); }
+extern "C" __global__ void aule_rope_f32(const RopeParams p) { rope_body<float>(p); }
+extern "C" __global__ void aule_rope_bf16(const RopeParams p) { rope_body<__nv_bfloat16>(p); }
+extern "C" __global__ void aule_rope_f16(const RopeParams p) { rope_body<__half>(p); }

@@ -17,17 +17,31 @@ struct SimtParams {
 };
 constexpr int SIMT_ROWS = 32, SIMT_LANES = 8;
 
+// ---- RoPE of Q and K in one launch (attn_simt.cu: aule_rope_*) -------------------------
+struct RopeParams {
+    const void* xq; void* oq; uint64_t rows_q; uint32_t Sq;     // [rows_q = B*Hq*Sq, D]
+    const void* xk; void* ok; uint64_t rows_k; uint32_t Sk;     // second tensor (rows_k = 0: none)
+    const float* cs; const float* sn;                           // [table_rows >= max(Sq, Sk), D/2] fp32
+    uint32_t D; int32_t mode;                                   // 0 half-split (Triton path), 1 interleaved pairs (Vulkan shader)
+    float sign;                                                 // -1: inverse rotation (backward)
+};
+
 // ---- tcgen05 forward (attn_fwd_sm100.cu) ----------------------------------------------
 struct FwdParams {
     float* lse;               // [B,Hq,Sq] fp32 or nullptr
-    void* o;                  // [B,Hq,Sq,D] output (v5 stores it from registers)
+    void* o;                  // [B,Hq,Sq,D_real] output (v5 stores it from registers)
     uint32_t B, Hq, Hkv, Sq, Sk;
+    uint32_t D_real;          // head_dim of the tensors in memory (<= the kernel's padded D; the TMA boxes zero-fill the rest)
     uint32_t num_q_super;     // ceil(Sq / 256)
     uint32_t num_tiles;       // num_q_super * Hq * B
     float scale;              // softmax scale (natural)
     float scale_log2;         // scale * log2(e)
-    int32_t causal;
-    int32_t window;           // > 0 with causal: key j visible to query i iff 0 <= i - j < window; <= 0: none
+    // Visibility: key j contributes to query i iff  i - win_left <= j <= i + win_right  (and j < Sk).
+    //   causal: win_right = 0; causal window W: win_left = W-1; bidirectional window W: win_left = win_right = W/2
+    //   (attention_f32.comp:173-183); "unbounded" = kWinInf.
+    uint32_t win_left, win_right;
+    int32_t causal;           // v4 kernel only
+    int32_t window;           // v4 kernel only
     int32_t pair_heads;       // 1: a work item is 128 rows x 2 adjacent q-heads of one KV group (equal trip counts);
                               // 0: 256 rows of one q-head
     uint32_t units_per_run;   // (batch, kv-head) units whose work items are scheduled together (L2 residency of K/V)
@@ -35,6 +49,7 @@ struct FwdParams {
     int32_t cross_item;       // v4 only: the first Q K^T of the next work item is issued under the current item's last block
     unsigned long long* trace; // bring-up: CTA 0 records (tag << 48 | clock64) events here (4 x 4096 entries) or nullptr
 };
+constexpr uint32_t kWinInf = 0x40000000u;
 
 // v5 layout: Q ring (3 tiles) | K/V ring (NS x [128 keys][D], K and V tiles interleaved, continuous across work
 // items) | row statistics | work descriptors (8 x 32 B) | mbarriers.  TMEM: one shared S buffer, P0, P1, O0, O1.

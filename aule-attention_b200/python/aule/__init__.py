@@ -75,11 +75,15 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
         query: [batch, heads_q, seq_len_q, head_dim] - torch.Tensor or numpy.ndarray
         key:   [batch, heads_kv, seq_len_k, head_dim]
         value: [batch, heads_kv, seq_len_k, head_dim]
-        rot_cos / rot_sin: accepted for signature parity; like the reference's GPU path
-            (__init__.py:204-207 does not forward them) they are not applied -- a warning is issued.
+        rot_cos / rot_sin: optional RoPE tables [.., seq_len, head_dim/2]; applied to Q and K before the attention with
+            the pairing of the backend that consumes them in the reference -- the Vulkan shader's adjacent pairs
+            (2i, 2i+1) (attention_f32.comp:98-111; the reference's Triton path drops them, __init__.py:204-207).
+            Use flash_attention_rope for the Triton half-split convention.
         causal: top-left aligned causal mask (default True)
         scale: softmax scale (default 1/sqrt(head_dim))
-        window_size: sliding window (-1 = full attention)
+        window_size: sliding window (-1 = full attention).  causal: key j visible iff 0 <= i-j < W; bidirectional:
+            |i-j| <= W//2 (the shader's convention, attention_f32.comp:173-183).  The reference's generic Triton
+            kernel keeps i-j <= W / |i-j| <= W (triton_flash.py:190-194): its W is W+1 (causal) / 2W (bidirectional) here.
 
     Returns: tensor with the shape (and dtype/device kind) of `query`.
     Raises: ValueError for invalid shapes; RuntimeError if no B200 backend is available.
@@ -88,9 +92,8 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
     if not _cuda_available:
         raise RuntimeError("aule (B200 build): CUDA sm_100 backend not available and there is no CPU fallback: "
                            + _backend_errors.get('cuda', 'unknown error'))
-    if rot_cos is not None or rot_sin is not None:
-        warnings.warn("rot_cos/rot_sin are not applied by flash_attention on the CUDA path "
-                      "(same as the reference's GPU path); apply RoPE before calling", stacklevel=2)
+    if (rot_cos is None) != (rot_sin is None):
+        raise ValueError("rot_cos and rot_sin must be given together")
     if _verbose:
         print(f"aule-attention: cuda-sm100 | shape={tuple(query.shape)} | causal={causal}")
 
@@ -103,6 +106,13 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
 
     if is_torch:
         from . import cuda_flash
+        if rot_cos is not None:
+            if not query.is_cuda:
+                query, key, value = (t.cuda() for t in (query, key, value))
+                return cuda_flash.flash_attention_rope(query, key, value, rot_cos, rot_sin, causal=causal, scale=scale,
+                                                       window_size=window_size, interleaved=True).cpu()
+            return cuda_flash.flash_attention_rope(query, key, value, rot_cos, rot_sin, causal=causal, scale=scale,
+                                                   window_size=window_size, interleaved=True)
         if query.is_cuda:
             return cuda_flash.flash_attention_cuda(query, key, value, causal=causal, scale=scale, window_size=window_size)
         # host tensors: staged through HBM by the library (still GPU compute, not a CPU fallback)
@@ -110,6 +120,11 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
         return out.to(query.dtype)
 
     import numpy as np
+    if rot_cos is not None:
+        if scale is not None:
+            raise ValueError("scale is not supported together with rot_cos/rot_sin on NumPy inputs (handle ABI, lib.zig:496-529)")
+        return Aule().attention(query, key, value, rot_cos=rot_cos, rot_sin=rot_sin, causal=causal,
+                                window_size=window_size).astype(query.dtype, copy=False)
     q = np.ascontiguousarray(query, dtype=np.float32)
     k = np.ascontiguousarray(key, dtype=np.float32)
     v = np.ascontiguousarray(value, dtype=np.float32)
@@ -128,14 +143,15 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
 attention = flash_attention      # alias, __init__.py:275
 
 
-def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1):
-    """RoPE (half-split convention) on Q and K, then attention -- reference: triton_flash.py:561-603."""
+def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1, interleaved=False):
+    """RoPE on Q and K, then attention -- reference: triton_flash.py:561-603 (half-split convention, the default);
+    interleaved=True selects the Vulkan shader's adjacent-pair convention (attention_f32.comp:98-111)."""
     from .cuda_flash import flash_attention_rope as _impl
     _validate(q, k, v)
     if not _cuda_available:
         raise RuntimeError("aule (B200 build): CUDA sm_100 backend not available and there is no CPU fallback: "
                            + _backend_errors.get('cuda', 'unknown error'))
-    return _impl(q, k, v, cos, sin, causal=causal, scale=scale, window_size=window_size)
+    return _impl(q, k, v, cos, sin, causal=causal, scale=scale, window_size=window_size, interleaved=interleaved)
 
 
 def flash_attention_paged(q, k_cache, v_cache, block_tables, context_lens, scale=None, window_size=-1,
@@ -172,8 +188,12 @@ def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.
     """Drop-in for torch.nn.functional.scaled_dot_product_attention. Falls back to the original
     SDPA for features outside the kernel (mask / dropout), same rule as __init__.py:321-347."""
     import torch
+    # Only shapes the tensor-core kernel takes are routed here (16-bit, head_dim <= 128 and a multiple of 8): anything
+    # that would land on the CUDA-core kernels (fp32, other head_dims) is SLOWER than the SDPA it would replace.
     needs_fallback = (attn_mask is not None or dropout_p > 0.0 or not _cuda_available or not query.is_cuda
-                      or query.dim() != 4 or query.shape[-1] > 128 or query.shape[-1] % 4 != 0
+                      or query.dim() != 4 or query.shape[-1] > 128 or query.shape[-1] % 8 != 0
+                      or query.dtype not in (torch.bfloat16, torch.float16)
+                      or key.dtype != query.dtype or value.dtype != query.dtype
                       or (is_causal and query.shape[-2] != key.shape[-2])      # SDPA's causal is top-left too, but be strict
                       or (query.shape[1] != key.shape[1] and not enable_gqa))
     if needs_fallback:

@@ -115,25 +115,48 @@ def flash_attention_host(q, k, v, causal=True, scale=None, window_size=-1, lse=N
 # =============================================================================
 # RoPE (mirror of triton_flash.py:561-703: flash_attention_rope, precompute_rope_frequencies, apply_rope_separate)
 # =============================================================================
+def _rope_tables(cos, sin, D, S, device):
+    """Validate and normalise cos/sin to contiguous fp32 [rows, D/2] on `device` (triton_flash.py:416-417 asserts
+    cos.shape[-1] == head_dim // 2).  A [S, D] "full-dim" table or a table shorter than the sequence is an error,
+    never a silent reinterpretation / out-of-bounds read."""
+    half = D // 2
+    if D % 2 != 0:
+        raise ValueError(f"RoPE needs an even head_dim, got {D}")
+    if cos is None or sin is None:
+        raise ValueError("cos and sin are required for RoPE")
+    if cos.shape[-1] != half or tuple(sin.shape) != tuple(cos.shape):
+        raise ValueError(f"cos/sin must have shape [..., seq_len, head_dim//2 = {half}] and match each other, "
+                         f"got cos {tuple(cos.shape)}, sin {tuple(sin.shape)}")
+    lead = 1
+    for n in cos.shape[:-2]:
+        lead *= int(n)
+    if lead != 1:
+        raise ValueError(f"cos/sin must not carry batch/head dimensions larger than 1, got {tuple(cos.shape)}")
+    cos = cos.reshape(-1, half).to(device=device, dtype=torch.float32).contiguous()
+    sin = sin.reshape(-1, half).to(device=device, dtype=torch.float32).contiguous()
+    if cos.shape[0] < S:
+        raise ValueError(f"cos/sin tables have {cos.shape[0]} rows, the sequence needs {S}")
+    return cos, sin
+
+
 class _RopeFunc(torch.autograd.Function):
-    """x -> RoPE(x) with the half-split convention (triton_flash.py:680-703). The backward pass is the
-    transposed rotation (same kernel, -sin)."""
+    """x -> RoPE(x), half-split (triton_flash.py:680-703) or interleaved (attention_f32.comp:98-111) convention.
+    The backward pass is the transposed rotation (same kernel, -sin)."""
 
     @staticmethod
-    def forward(ctx, x, cos, sin):
+    def forward(ctx, x, cos, sin, interleaved):
         lib = ffi.ensure_init()
         B, H, S, D = x.shape
         cdt = x.dtype if x.dtype in _TORCH_TO_AULE else torch.float32
         xc = x.to(cdt).contiguous()
-        cos = cos.reshape(-1, D // 2)[:S].to(device=x.device, dtype=torch.float32).contiguous()
-        sin = sin.reshape(-1, D // 2)[:S].to(device=x.device, dtype=torch.float32).contiguous()
+        cos, sin = _rope_tables(cos, sin, D, S, x.device)
         out = torch.empty_like(xc)
         dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
-        rc = lib.aule_rope_dptr(xc.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, H, S, D,
-                                _TORCH_TO_AULE[cdt], 0, dev, torch.cuda.current_stream(dev).cuda_stream)
+        rc = lib.aule_rope_dptr(xc.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, H, S, D, cos.shape[0],
+                                1 if interleaved else 0, _TORCH_TO_AULE[cdt], 0, dev, torch.cuda.current_stream(dev).cuda_stream)
         _check(rc, "RoPE failed")
         ctx.save_for_backward(cos, sin)
-        ctx.dev, ctx.cdt, ctx.orig = dev, cdt, x.dtype
+        ctx.dev, ctx.cdt, ctx.orig, ctx.interleaved = dev, cdt, x.dtype, bool(interleaved)
         return out.to(x.dtype)
 
     @staticmethod
@@ -143,28 +166,50 @@ class _RopeFunc(torch.autograd.Function):
         B, H, S, D = g.shape
         gc = g.to(ctx.cdt).contiguous()
         out = torch.empty_like(gc)
-        rc = lib.aule_rope_dptr(gc.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, H, S, D,
-                                _TORCH_TO_AULE[ctx.cdt], 1, ctx.dev, torch.cuda.current_stream(ctx.dev).cuda_stream)
+        rc = lib.aule_rope_dptr(gc.data_ptr(), out.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, H, S, D, cos.shape[0],
+                                1 if ctx.interleaved else 0, _TORCH_TO_AULE[ctx.cdt], 1, ctx.dev,
+                                torch.cuda.current_stream(ctx.dev).cuda_stream)
         _check(rc, "RoPE backward failed")
-        return out.to(ctx.orig), None, None
+        return out.to(ctx.orig), None, None, None
 
 
-def apply_rope(x, cos, sin):
+def apply_rope(x, cos, sin, interleaved=False):
     """RoPE on the GPU through the C ABI (differentiable)."""
-    return _RopeFunc.apply(x, cos, sin)
+    return _RopeFunc.apply(x, cos, sin, interleaved)
 
 
-def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1):
-    """Mirror of triton_flash.py:561-603: RoPE on Q and K (half-split convention), then the fused attention.
-    The rotation is a separate memory-bound pass over Q and K here (2 x (|Q|+|K|) bytes), not fused into the
-    tcgen05 kernel, which reads its operands with TMA straight into the MMA layout."""
+def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1, interleaved=False):
+    """Mirror of triton_flash.py:561-603: RoPE on Q and K, then the fused attention.
+
+    Inference (no gradient needed): one C call, aule_attention_forward_rope_dptr -- a single launch reads Q and K once
+    and writes their rotated copies once (stream-ordered workspace), then the tcgen05 kernel runs on them.  K has to be
+    rotated once per key, not once per (query block, key) pair, so the rotation is a prologue of the kernel's K/V stream,
+    not a part of it.  With autograd: apply_rope (differentiable) + the attention Function.
+    `interleaved=True` selects the Vulkan shader's pairing (attention_f32.comp:98-111)."""
     assert q.dim() == 4 and k.dim() == 4 and v.dim() == 4
     assert q.shape[-1] == k.shape[-1] == v.shape[-1]
     assert k.shape[1] == v.shape[1] and k.shape[2] == v.shape[2]
     assert q.shape[1] % k.shape[1] == 0
     assert cos is not None and sin is not None, "cos and sin are required for RoPE"
-    return flash_attention_cuda(apply_rope(q, cos, sin), apply_rope(k, cos, sin), v, causal=causal, scale=scale,
-                                window_size=window_size)
+    B, Hq, Sq, D = q.shape
+    _, Hkv, Sk, _ = k.shape
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v))
+    if needs_grad:
+        return flash_attention_cuda(apply_rope(q, cos, sin, interleaved), apply_rope(k, cos, sin, interleaved), v,
+                                    causal=causal, scale=scale, window_size=window_size)
+    lib = ffi.ensure_init()
+    cos, sin = _rope_tables(cos, sin, D, max(Sq, Sk), q.device)
+    orig = q.dtype
+    cdt = orig if orig in (torch.bfloat16, torch.float16) else torch.float32
+    q, k, v = (t.to(cdt).contiguous() for t in (q, k, v))
+    out = torch.empty_like(q)
+    dev = q.device.index if q.device.index is not None else torch.cuda.current_device()
+    rc = lib.aule_attention_forward_rope_dptr(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), 0, cos.data_ptr(),
+                                              sin.data_ptr(), cos.shape[0], 1 if interleaved else 0, B, Hq, Hkv, Sq, Sk, D,
+                                              _TORCH_TO_AULE[cdt], float(scale) if scale else 0.0, 1 if causal else 0,
+                                              int(window_size), dev, torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc, "Attention failed")
+    return out.to(orig)
 
 
 def precompute_rope_frequencies(seq_len, head_dim, base=10000.0, device="cuda", dtype=torch.float32):

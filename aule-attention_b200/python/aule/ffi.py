@@ -70,7 +70,11 @@ def _proto(lib):
         "aule_attention_forward_dptr": ([u64] * 5 + [u32] * 6 + [i32, c.c_float, i32, i32, i32, u64], i32),
         "aule_attention_backward_dptr": ([u64] * 9 + [u32] * 6 + [i32, c.c_float, i32, i32, u64], i32),
         "aule_attention_forward_host": ([vp, vp, vp, vp, fp] + [u32] * 6 + [i32, c.c_float, i32, i32, i32], i32),
-        "aule_rope_dptr": ([u64] * 4 + [u32] * 4 + [i32, i32, i32, u64], i32),
+        "aule_attention_backward_host": ([vp] * 5 + [fp] + [vp] * 3 + [u32] * 6 + [i32, c.c_float, i32, i32], i32),
+        "aule_rope_dptr": ([u64] * 4 + [u32] * 5 + [i32, i32, i32, i32, u64], i32),
+        "aule_attention_forward_rope_dptr": ([u64] * 7 + [u32, i32] + [u32] * 6 + [i32, c.c_float, i32, i32, i32, u64], i32),
+        "aule_attention_forward_spanning_dptr": ([u64] * 5 + [u32] * 6 + [i32, c.c_float, i32, i32, i32, u64,
+                                                  c.POINTER(i32), i32, i32, fp], i32),
         "aule_attention_paged_decode_dptr": ([u64] * 6 + [u32] * 8 + [i32, c.c_float, i32, i32, u64], i32),
         "aule_device_count": ([], i32), "aule_get_sm_count": ([i32], i32), "aule_synchronize": ([i32], i32),
         "aule_launch_count": ([], u64), "aule_last_kernel": ([], c.c_char_p), "aule_version": ([], c.c_char_p),
@@ -149,6 +153,10 @@ class GpuTensor:
         if self._handle != 0:
             self._aule._lib.aule_tensor_destroy(ctypes.c_uint64(self._handle))
             self._handle = 0
+            try:
+                self._aule._tensors.remove(self)
+            except ValueError:
+                pass
 
 
 class Aule:
@@ -241,11 +249,22 @@ class Aule:
             raise ValueError(f"heads_q ({Hq}) must be divisible by heads_kv ({Hkv}) for GQA")
         if D > 128:
             raise ValueError(f"head_dim must be <= 128. Got {D}")
-        if rot_cos is not None or rot_sin is not None:
-            raise AuleError("fused RoPE is not part of the B200 hot path")
         q = np.ascontiguousarray(query, dtype=np.float32)
         k = np.ascontiguousarray(key, dtype=np.float32)
         v = np.ascontiguousarray(value, dtype=np.float32)
+        if rot_cos is not None or rot_sin is not None:
+            # vulkan.py:717-790: NumPy cos/sin [.., seq, head_dim/2] -> device tensors -> attention_gpu (interleaved pairs)
+            if rot_cos is None or rot_sin is None:
+                raise ValueError("rot_cos and rot_sin must be given together")
+            half = D // 2
+            cos = np.ascontiguousarray(rot_cos, dtype=np.float32).reshape(1, 1, -1, half)
+            sin = np.ascontiguousarray(rot_sin, dtype=np.float32).reshape(1, 1, -1, half)
+            with Aule() as ctx:
+                tq, tk, tv, to = ctx.tensor(q.shape), ctx.tensor(k.shape), ctx.tensor(v.shape), ctx.tensor(q.shape)
+                tc, ts = ctx.tensor(cos.shape), ctx.tensor(sin.shape)
+                tq.upload(q); tk.upload(k); tv.upload(v); tc.upload(cos); ts.upload(sin)
+                ctx.attention_gpu(tq, tk, tv, to, rot_cos=tc, rot_sin=ts, causal=causal, window_size=window_size)
+                return to.download()
         out = np.empty_like(q)
         rc = self._lib.aule_attention_forward_host(q.ctypes.data, k.ctypes.data, v.ctypes.data, out.ctypes.data, None,
                                                    B, Hq, Hkv, Sq, Sk, D, DTYPE_F32, 0.0, 1 if causal else 0,
@@ -290,7 +309,7 @@ class Aule:
         raise AuleError("attention_gravity is outside the B200 hot path (unsupported)")
 
     def close(self):
-        for t in self._tensors:
+        for t in list(self._tensors):
             t.destroy()
         self._tensors = []
 

@@ -135,10 +135,13 @@ enum { AULE_DTYPE_F32 = 0, AULE_DTYPE_BF16 = 1, AULE_DTYPE_F16 = 2 };
  *   q,o: [B,Hq,Sq,D]  k,v: [B,Hkv,Sk,D]  lse_or_0: [B,Hq,Sq] fp32 or 0
  *   scale <= 0  => 1/sqrt(D)      (triton_flash.py:394-395)
  *   causal      => key j visible to query i iff j <= i (top-left, :187)
- *   window      => -1 full; W>0 keeps 0 <= i-j < W (attention_f32.comp:176-178)
+ *   window      => -1 full; W>0 causal keeps 0 <= i-j < W, bidirectional keeps |i-j| <= W/2 (the Vulkan shader's
+ *                  convention, attention_f32.comp:173-183; the generic Triton kernel's W (triton_flash.py:190-194:
+ *                  i-j <= W, |i-j| <= W) is W+1 causal / 2W bidirectional here)
  *   GQA         => kv_head = q_head / (Hq/Hkv)          (triton_flash.py:95-96)
- * bf16/fp16 with D in {64,128} run the tcgen05/TMA kernel; every other
- * (dtype, D<=128, D%4==0) runs the fp32-accumulate CUDA-core kernel.
+ * bf16/fp16 with D <= 128, D % 8 == 0 run the tcgen05/TMA kernel (D is zero-padded to 64 / 128 by the TMA boxes,
+ * like BLOCK_K = next_power_of_2(D) in triton_flash.py:446); fp32 and D % 8 != 0 run the fp32-accumulate CUDA-core
+ * kernel (AULE_LOG=1 reports that choice on stderr).
  * Replaces _flash_attn_fwd_kernel launch, triton_flash.py:448-464. */
 AULE_API int32_t aule_attention_forward_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o,
                                              uint64_t lse_or_0, uint32_t B, uint32_t Hq, uint32_t Hkv,
@@ -159,7 +162,9 @@ AULE_API int32_t aule_attention_backward_dptr(uint64_t q, uint64_t k, uint64_t v
 
 /* Host-buffer forward for any dtype: stages through device memory with the
  * H2D copy of batch b+1 / D2H copy of batch b-1 overlapped with the kernel of
- * batch b (pinned staging, 3 streams).  Synchronous.  lse may be NULL.
+ * batch b (3 streams).  Page-locked caller buffers are copied directly; pageable ones (NumPy arrays) go through the
+ * library's own pinned bounce buffers, double-buffered per chunk.  Synchronous.  lse may be NULL.
+ * Thread-safe: host-pointer entries are serialised per device, device-pointer entries may run concurrently.
  * This is the call bench.py times for the end-to-end ("e2e") figure. */
 AULE_API int32_t aule_attention_forward_host(const void* q, const void* k, const void* v, void* o,
                                              float* lse_or_null, uint32_t B, uint32_t Hq,
@@ -167,14 +172,47 @@ AULE_API int32_t aule_attention_forward_host(const void* q, const void* k, const
                                              int32_t dtype, float scale, int32_t causal,
                                              int32_t window, int32_t device);
 
-/* Rotary position embedding on raw device pointers, the half-split convention of the reference's
- * Triton path (python/aule/triton_flash.py:680-703 apply_rope_separate):
- *   out[d] = x[d] cos[s,d] - x[d+D/2] sin[s,d],  out[d+D/2] = x[d+D/2] cos[s,d] + x[d] sin[s,d]
- * x/out: [B,H,S,D] of `dtype`, cos/sin: [S, D/2] fp32; inverse != 0 applies the transpose (backward pass).
- * The step immediately before the hot path (flash_attention_rope, triton_flash.py:561-603). */
+/* Host-buffer backward for any dtype (q,k,v,o,dO,lse in; dq,dk,dv out), staged through device memory.  Synchronous.
+ * The typed twin of aule_attention_backward (lib.zig:639-762), used by bench.py for the forward+backward e2e figure. */
+AULE_API int32_t aule_attention_backward_host(const void* q, const void* k, const void* v, const void* o,
+                                              const void* d_o, const float* lse, void* dq, void* dk, void* dv,
+                                              uint32_t B, uint32_t Hq, uint32_t Hkv, uint32_t Sq, uint32_t Sk,
+                                              uint32_t D, int32_t dtype, float scale, int32_t causal, int32_t device);
+
+/* Rotary position embedding on raw device pointers.  Two pairing conventions, as in the reference:
+ *   interleaved == 0, half-split (Triton path, python/aule/triton_flash.py:680-703 apply_rope_separate):
+ *     out[d] = x[d] cos[s,d] - x[d+D/2] sin[s,d],  out[d+D/2] = x[d+D/2] cos[s,d] + x[d] sin[s,d]
+ *   interleaved != 0, adjacent pairs (Vulkan shader, shaders/attention_f32.comp:98-111; tests/test_rope_unit.py:76-85):
+ *     out[2d] = x[2d] cos[s,d] - x[2d+1] sin[s,d],  out[2d+1] = x[2d] sin[s,d] + x[2d+1] cos[s,d]
+ * x/out: [B,H,S,D] of `dtype`, cos/sin: [table_rows, D/2] fp32 with table_rows >= S (checked: a short table is an error,
+ * never an out-of-bounds read); inverse != 0 applies the transpose (backward pass). */
 AULE_API int32_t aule_rope_dptr(uint64_t x, uint64_t out, uint64_t cos, uint64_t sin, uint32_t B, uint32_t H,
-                                uint32_t S, uint32_t D, int32_t dtype, int32_t inverse, int32_t device,
-                                uint64_t cu_stream);
+                                uint32_t S, uint32_t D, uint32_t table_rows, int32_t interleaved, int32_t dtype,
+                                int32_t inverse, int32_t device, uint64_t cu_stream);
+
+/* RoPE prologue + fused attention behind one call (flash_attention_rope, triton_flash.py:561-603; the handle form is
+ * aule_attention_forward_gpu with rot_cos / rot_sin, lib.zig:496-529).  Q and K are rotated by ONE launch that reads each
+ * of them once and writes the rotated copy once into a stream-ordered workspace (K must be rotated once per key, not once
+ * per (query block, key) pair, so the rotation cannot live in the attention kernel's K/V stream), then the fused kernel
+ * runs on the copies.  Arguments as aule_attention_forward_dptr + the tables of aule_rope_dptr. */
+AULE_API int32_t aule_attention_forward_rope_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse_or_0,
+                                                  uint64_t cos, uint64_t sin, uint32_t table_rows, int32_t interleaved,
+                                                  uint32_t B, uint32_t Hq, uint32_t Hkv, uint32_t Sq, uint32_t Sk,
+                                                  uint32_t D, int32_t dtype, float scale, int32_t causal,
+                                                  int32_t window, int32_t device, uint64_t cu_stream);
+
+/* One call spanning several devices of the box (SURVEY 8e "spanning call"): q,k,v,o (and lse) live on `src_device`;
+ * the (batch, kv-head) units are split contiguously over devices[0..num_devices) (src_device must be one of them).
+ * Every other device receives its Q/K/V slabs over NVLink (cuMemcpyPeerAsync), runs the fused kernel and returns its
+ * O / LSE slab; `chunks` sub-ranges per device overlap copy-in, kernel and copy-out (1 = strictly serial phases).
+ * The caller's stream waits for the gathered result.  timings_ms_or_null -> float[4]: scatter, kernel, gather (max over
+ * devices of each phase's device-timed duration) and the total on the source stream (the call then blocks). */
+AULE_API int32_t aule_attention_forward_spanning_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t lse_or_0,
+                                                      uint32_t B, uint32_t Hq, uint32_t Hkv, uint32_t Sq, uint32_t Sk,
+                                                      uint32_t D, int32_t dtype, float scale, int32_t causal,
+                                                      int32_t window, int32_t src_device, uint64_t cu_stream,
+                                                      const int32_t* devices, int32_t num_devices, int32_t chunks,
+                                                      float* timings_ms_or_null);
 
 /* Paged-KV decode on raw device pointers: one query token per sequence against a block-table
  * KV cache in the vLLM layout.  Replaces flash_attention_paged_amd / _paged_attention_fwd_amd

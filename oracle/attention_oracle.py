@@ -77,16 +77,19 @@ def _mask(seq_q, seq_k, causal, window, row0=0):
     """Boolean [rows, seq_k] 'masked-out' matrix. Causal is TOP-LEFT aligned:
     key j is visible to query i iff j <= i (triton_flash.py:187,
     attention_f32.comp:169, __init__.py:262, attention_ref.zig:120).
-    Sliding window (causal): keep i - j < window (attention_f32.comp:176-178)."""
+    Sliding window, the Vulkan shader's convention (attention_f32.comp:173-183): causal keeps i - j < window,
+    bidirectional keeps |i - j| <= window // 2.  (The reference's generic Triton kernel keeps i - j <= W and
+    |i - j| <= W, triton_flash.py:190-194: its W is window = W + 1 causal, window = 2 W bidirectional here.)"""
     i = np.arange(row0, row0 + seq_q)[:, None]
     j = np.arange(seq_k)[None, :]
     m = np.zeros((seq_q, seq_k), dtype=bool)
     if causal:
         m |= j > i
     if window is not None and window > 0:
-        m |= (i - j) >= window
-        if not causal:
-            m |= (j - i) >= window
+        if causal:
+            m |= (i - j) >= window
+        else:
+            m |= np.abs(i - j) > (window // 2)
     return m
 
 
@@ -168,15 +171,37 @@ def attention_bwd_ref(q, k, v, do, causal=True, scale=None, acc=np.float64):
     return dq, dk, dv, o, lse
 
 
-def rope_ref(x, cos, sin):
-    """Half-split RoPE, restating apply_rope_separate (python/aule/triton_flash.py:680-703):
-    x_rot = x * [cos,cos] + rotate_half(x) * [sin,sin], rotate_half(x) = [-x2, x1]. x: [B,H,S,D], cos/sin: [S,D/2]."""
+def rope_ref(x, cos, sin, interleaved=False):
+    """RoPE in fp64. x: [B,H,S,D], cos/sin: [>=S, D/2].
+    Half-split (default), restating apply_rope_separate (python/aule/triton_flash.py:680-703):
+        x_rot = x * [cos,cos] + rotate_half(x) * [sin,sin], rotate_half(x) = [-x2, x1].
+    interleaved=True, restating the Vulkan shader (shaders/attention_f32.comp:98-111) and the torch formula of the
+    reference's own test (tests/test_rope_unit.py:76-85): pairs (2i, 2i+1),
+        out[2i] = x[2i] cos_i - x[2i+1] sin_i,  out[2i+1] = x[2i] sin_i + x[2i+1] cos_i."""
     x = np.asarray(x, np.float64)
     S, D = x.shape[2], x.shape[3]
-    c = np.concatenate([cos[:S], cos[:S]], axis=-1)[None, None].astype(np.float64)
-    s = np.concatenate([sin[:S], sin[:S]], axis=-1)[None, None].astype(np.float64)
+    cos = np.asarray(cos, np.float64).reshape(-1, D // 2)[:S]
+    sin = np.asarray(sin, np.float64).reshape(-1, D // 2)[:S]
+    if interleaved:
+        x1, x2 = x[..., 0::2], x[..., 1::2]
+        out = np.empty_like(x)
+        out[..., 0::2] = x1 * cos[None, None] - x2 * sin[None, None]
+        out[..., 1::2] = x1 * sin[None, None] + x2 * cos[None, None]
+        return out
+    c = np.concatenate([cos, cos], axis=-1)[None, None]
+    s = np.concatenate([sin, sin], axis=-1)[None, None]
     x1, x2 = x[..., :D // 2], x[..., D // 2:]
     return x * c + np.concatenate([-x2, x1], axis=-1) * s
+
+
+def allclose_zig(got, exp, atol, rtol, floor=1e-6):
+    """The reference's comparison (tests/test_attention.zig:60-77 compareArrays): an element passes when
+    |got-exp| < atol OR |got-exp| / max(|exp|, floor) < rtol.  Returns (ok, number of failing elements, worst abs, worst rel)."""
+    got, exp = np.asarray(got, np.float64), np.asarray(exp, np.float64)
+    ad = np.abs(got - exp)
+    rd = ad / np.maximum(np.abs(exp), floor)
+    bad = ~((ad < atol) | (rd < rtol))
+    return (not bad.any()), int(bad.sum()), float(ad.max()), float(rd[ad >= atol].max() if (ad >= atol).any() else 0.0)
 
 
 # --------------------------------------------------------------------------
