@@ -288,6 +288,17 @@ int32_t aule_attention_backward_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_
     return 0;
 }
 
+int32_t aule_attention_backward_window_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t d_o, uint64_t lse,
+                                            uint64_t dq, uint64_t dk, uint64_t dv, uint32_t B, uint32_t Hq, uint32_t Hkv,
+                                            uint32_t Sq, uint32_t Sk, uint32_t D, int32_t dtype, float scale, int32_t causal,
+                                            int32_t window, int32_t device, uint64_t cu_stream) {
+    if (!g_engine.ready()) { set_error("Library not initialized. Call aule_init() first."); return -1; }
+    aule::AttnShape s{B, Hq, Hkv, Sq, Sk, D};
+    std::string e = g_engine.backward(device, (CUstream)cu_stream, q, k, v, o, d_o, lse, dq, dk, dv, s, dtype, scale, causal != 0, window);
+    if (!e.empty()) { set_error("Backward pass failed: %s", e.c_str()); return -4; }
+    return 0;
+}
+
 int32_t aule_attention_forward_host(const void* q, const void* k, const void* v, void* o, float* lse_or_null,
                                     uint32_t B, uint32_t Hq, uint32_t Hkv, uint32_t Sq, uint32_t Sk, uint32_t D,
                                     int32_t dtype, float scale, int32_t causal, int32_t window, int32_t device) {

@@ -391,7 +391,7 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
 
 std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
                              CUdeviceptr d_o, CUdeviceptr lse, CUdeviceptr dq, CUdeviceptr dk, CUdeviceptr dv,
-                             const AttnShape& s, int32_t dtype, float scale, bool causal) {
+                             const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window) {
     if (!ready_) return "Library not initialized. Call aule_init() first.";
     Device* dp = by_ordinal(dev);
     if (!dp) return "invalid device index";
@@ -406,8 +406,14 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     const size_t dbytes = (size_t)s.B * s.Hq * s.Sq * sizeof(float);
     if (!(e = check(drv_.cuMemAllocAsync(&delta, dbytes, stream), "cuMemAllocAsync(delta)")).empty()) return e;
 
-    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && path_ != kForceCudaCore &&
+    if (window == 0) window = -1;
+    // Tensor-core backward: 16-bit, D in {64,128}, causal / full masks.  A sliding window (the reference's backward ignores
+    // it, triton_flash.py:313-319 -- its gradients are then wrong) and other head dims run the deterministic CUDA-core kernels.
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && path_ != kForceCudaCore && window < 0 &&
                     ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0;
+    if (!tc && log_enabled())
+        fprintf(stderr, "[aule] backward [%u,%u(%u),%u/%u,%u] %s: CUDA-core kernels (%s)\n", s.B, s.Hq, s.Hkv, s.Sq, s.Sk, s.D,
+                kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : window > 0 ? "sliding window" : "head_dim not 64/128 or unaligned pointers");
     if (tc) {
         // Tensor-core backward: Delta pre-pass, then the dK/dV kernel (key block outer) and the dQ kernel (query block
         // outer).  No atomics and no workspace beyond Delta: bit-reproducible.
@@ -487,7 +493,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     p.lse = (float*)lse; p.d_o = (const void*)d_o;
     p.dq = (void*)dq; p.dk = (void*)dk; p.dv = (void*)dv; p.delta = (float*)delta;
     p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.Sq = s.Sq; p.Sk = s.Sk; p.D = s.D;
-    p.scale = scale; p.causal = causal ? 1 : 0; p.window = -1;
+    p.scale = scale; p.causal = causal ? 1 : 0; p.window = window;
     void* params[] = {&p};
     char name[64];
     const unsigned threads = aule_kp::SIMT_ROWS * aule_kp::SIMT_LANES;
@@ -564,15 +570,32 @@ std::string Engine::forward_host(int dev, const void* q, const void* k, const vo
     if (!(e = ensure_stage(d, 3, q_unit * units)).empty()) return e;
     if (lse && !(e = ensure_stage(d, 4, lse_unit * units)).empty()) return e;
 
-    // Chunk over units so that copy-in of chunk c+1, the kernel of chunk c and copy-out of
-    // chunk c-1 overlap (three streams, persistent events between them).
-    // 8 chunks measured best on config C (9.04 ms per call; 16: 9.20, 32: 10.06 -- per-copy overheads outgrow the
-    // shorter fill/drain of the pipeline); AULE_HOST_CHUNKS overrides (tuning hook).
-    uint32_t want_chunks = 8;
-    if (const char* ov = getenv("AULE_HOST_CHUNKS")) { const long v_ = atol(ov); if (v_ > 0) want_chunks = (uint32_t)v_; }
-    want_chunks = std::min<uint32_t>(want_chunks, Device::kMaxChunks);
-    const uint32_t nchunks = std::min<uint32_t>(units, want_chunks);
-    const uint32_t per = (units + nchunks - 1) / nchunks;
+    // Chunk over units so that copy-in of chunk c+1, the kernel of chunk c and copy-out of chunk c-1 overlap (three streams,
+    // persistent events between them).  The call is bound by the H2D copies (Q+K+V in, only O out; PCIe is full duplex), so
+    // what is left after the last upload -- the last chunk's kernel and download -- is pure tail: chunk sizes shrink
+    // geometrically (a quarter of what remains, down to one unit) so that the tail is one unit's worth, while the early
+    // chunks stay large (uniform 8 chunks: 8.85 ms per config-C call against 7.84 ms for the bare copies; 16 / 32 uniform
+    // chunks were slower, per-copy overheads).  AULE_HOST_CHUNKS=n forces n uniform chunks (tuning hook).
+    std::vector<uint32_t> bounds{0};
+    {
+        uint32_t forced = 0;
+        if (const char* ov = getenv("AULE_HOST_CHUNKS")) { const long v_ = atol(ov); if (v_ > 0) forced = (uint32_t)std::min<long>(v_, Device::kMaxChunks); }
+        if (forced) {
+            const uint32_t nch = std::min(units, forced), per_ = (units + nch - 1) / nch;
+            for (uint32_t u = per_; u < units; u += per_) bounds.push_back(u);
+        } else {
+            uint32_t done = 0;
+            while (done < units && bounds.size() < Device::kMaxChunks) {
+                const uint32_t left = units - done;
+                done += std::max<uint32_t>(1, (left + 3) / 4);
+                if (done < units) bounds.push_back(done);
+            }
+        }
+        bounds.push_back(units);
+    }
+    const uint32_t nchunks = (uint32_t)bounds.size() - 1;
+    uint32_t per = 0;                                              // largest chunk (sizes the bounce buffers)
+    for (uint32_t c = 0; c < nchunks; ++c) per = std::max(per, bounds[c + 1] - bounds[c]);
 
     // Pageable callers (every NumPy caller of the legacy ABI): the DMA engines cannot read pageable memory, and the
     // driver's own fallback is a synchronous staged copy.  Stage through the library's pinned bounce buffers instead,
@@ -603,9 +626,7 @@ std::string Engine::forward_host(int dev, const void* q, const void* k, const vo
 
     int code = 0;
     for (uint32_t c = 0; c < nchunks && e.empty(); ++c) {
-        const uint32_t u0 = c * per;
-        if (u0 >= units) break;
-        const uint32_t nu = std::min(per, units - u0);
+        const uint32_t u0 = bounds[c], nu = bounds[c + 1] - bounds[c];
         code = -3;
         if (in_pinned) {
             e = check(drv_.cuMemcpyHtoDAsync(d.stage[0] + u0 * q_unit, (const char*)q + u0 * q_unit, nu * q_unit, d.s_in), "upload Q");
@@ -690,7 +711,7 @@ std::string Engine::backward_host(int dev, const void* q, const void* k, const v
         if (!(e = check(drv_.cuMemcpyHtoDAsync(d.stage[i], src[i], sizes[i], d.s_compute), "upload")).empty()) return e;
     *stage_code = -4;
     e = backward(dev, d.s_compute, d.stage[0], d.stage[1], d.stage[2], d.stage[3], d.stage[5], d.stage[4], d.stage[6],
-                 d.stage[7], d.stage[8], s, dtype, scale, causal);
+                 d.stage[7], d.stage[8], s, dtype, scale, causal, -1);
     if (!e.empty()) return e;
     void* dst[3] = {dq, dk, dv};
     for (int i = 0; i < 3; ++i)

@@ -103,7 +103,7 @@ public:
                         CUdeviceptr lse, const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window);
     std::string backward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr k, CUdeviceptr v, CUdeviceptr o,
                          CUdeviceptr d_o, CUdeviceptr lse, CUdeviceptr dq, CUdeviceptr dk, CUdeviceptr dv,
-                         const AttnShape& s, int32_t dtype, float scale, bool causal);
+                         const AttnShape& s, int32_t dtype, float scale, bool causal, int32_t window = -1);
     // Synchronous, host pointers, chunked + pipelined over (batch x kv-head) units.
     // `stage_code` receives the reference's failure stage (-2 alloc, -3 upload, -4 compute, -5 download).
     std::string forward_host(int dev, const void* q, const void* k, const void* v, void* o, float* lse,

@@ -41,6 +41,9 @@ template <int D> using Cfg = aule_kp::BwdCfg<D>;
 #ifndef AULE_BWD_TRACE
 #define AULE_BWD_TRACE 0
 #endif
+#ifndef AULE_BWD_XPASS
+#define AULE_BWD_XPASS 0          // 1: scale/offset pass of its own before the exp2 loop of the P phase (A/B: tools/gpu/r2_exp11.sh)
+#endif
 struct Tracer {
 #if AULE_BWD_TRACE
     unsigned long long* buf;
@@ -64,9 +67,23 @@ template <bool MASK, int EMU = 0>
 __device__ __forceinline__ void p_from_s(const uint32_t (&s)[32], float* pv, float c2, float lse2, uint32_t col0, uint32_t row,
                                          uint32_t Sk, bool row_ok, bool diag) {
     const float2 cc = make_float2(c2, c2), nl = make_float2(-lse2, -lse2);
+#if AULE_BWD_XPASS
+    uint32_t xs[32];
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
         const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), cc, nl);
+        xs[e] = __float_as_uint(x.x); xs[e + 1] = __float_as_uint(x.y);
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(xs[e]));
+#endif
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+#if AULE_BWD_XPASS
+        const float2 x = make_float2(__uint_as_float(xs[e]), __uint_as_float(xs[e + 1]));
+#else
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), cc, nl);
+#endif
         float2 v;
         if (((e >> 1) & 3) < EMU) {
             v = ex2_emu2(x);
@@ -680,13 +697,32 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 tmem_wait_ld();
                 tr.ev(22, step);
                 const float2 cc = make_float2(p.scale_log2, p.scale_log2);
+#if AULE_BWD_XPASS
+                // x = S^T*scale_log2 - lse2 in a pass of its own (in place) before the exp2 loop: an FFMA2 in front of every
+                // MUFU pair costs far more than its issue slots (profiles/r2_fwd_softmax_loop.md)
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(sc + 4 * e4);       // broadcast
+                    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
+                    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
+                    s[4 * e4] = __float_as_uint(x0.x); s[4 * e4 + 1] = __float_as_uint(x0.y);
+                    s[4 * e4 + 2] = __float_as_uint(x1.x); s[4 * e4 + 3] = __float_as_uint(x1.y);
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) asm volatile("" : "+r"(s[e]));
+#endif
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {               // 16 query columns each: publish, then the next 16
 #pragma unroll
                     for (int e4 = 4 * half; e4 < 4 * half + 4; ++e4) {
+#if AULE_BWD_XPASS
+                        const float2 x0 = make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1]));
+                        const float2 x1 = make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3]));
+#else
                         const float4 l4 = *reinterpret_cast<const float4*>(sc + 4 * e4);       // broadcast
                         const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4]), __uint_as_float(s[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
                         const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(s[4 * e4 + 2]), __uint_as_float(s[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
+#endif
                         float2 v0, v1;
                         if ((e4 & 1) == 0) { v0 = ex2_emu2(x0); } else { v0.x = ex2(x0.x); v0.y = ex2(x0.y); }   // 1 pair in 4 on the FMA pipe
                         v1.x = ex2(x1.x); v1.y = ex2(x1.y);

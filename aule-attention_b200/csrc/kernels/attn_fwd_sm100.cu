@@ -217,6 +217,16 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV);
     }
     if (warp == 14) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    if constexpr (C::ROWSUM_MMA) {
+        // constant tile [128 keys][64 cols], MN-major 128B-swizzled like a V chunk: column 0 = 1.0, the rest 0
+        uint4* ones = reinterpret_cast<uint4*>(smem + C::OFF_ONES);
+        for (uint32_t i = threadIdx.x; i < C::CHUNK_BYTES / 16; i += blockDim.x) {
+            const uint32_t krow = i >> 3, unit = i & 7;                 // 8 16-byte units per key row; column 0 lives in unit (0 ^ (krow & 7))
+            const uint32_t one = BF16 ? 0x3F80u : 0x3C00u;
+            ones[i] = make_uint4(unit == (krow & 7) ? one : 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -225,7 +235,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     constexpr uint64_t HI_K = smem_desc_hi(16, 1024);                   // K-major SW128 (Q, K)
     constexpr uint64_t HI_V = smem_desc_hi(C::CHUNK_BYTES, 1024);       // MN-major SW128 (V)
     constexpr uint32_t IDESC_QK = instr_desc_f16(BF16, 128, 128, false);
-    constexpr uint32_t IDESC_PV = instr_desc_f16(BF16, 128, D, true);
+    constexpr uint32_t IDESC_PV = instr_desc_f16(BF16, 128, C::PV_N, true);
 
     constexpr bool SO = (VAR & 256) != 0;   // softmax-only microbenchmark: no MMA / TMA / epilogue, no barriers (tools/softmax_only.py)
     if (warp < 8) {
@@ -358,6 +368,14 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                             tmem_st32(tO + c * 32, o);
                         }
+                        if constexpr (C::ROWSUM_MMA) {                    // the row-sum column rides with O
+                            uint32_t o[16];
+                            tmem_ld16(tO + D, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st16(tO + D, o);
+                        }
                     }
                 }
                 tr.ev(13, g);
@@ -418,7 +436,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                             e.x = ex2(x.x);
                             e.y = ex2(x.y);
                         }
-                        if (!(VAR & 32768)) { if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e); }
+                        if (!(VAR & 32768) && !C::ROWSUM_MMA) { if (i & 1) acc1 = __fadd2_rn(acc1, e); else acc0 = __fadd2_rn(acc0, e); }
                         pk[c][i] = (BF16 && TRUNC_PACK) ? __byte_perm(__float_as_uint(e.x), __float_as_uint(e.y), 0x7632) : pack2<BF16>(e.x, e.y);
                     }
                     if constexpr (VAR & 2) {                        // one publish per block
@@ -483,16 +501,22 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
                 mbar_wait(bar(B_STFULL + t), it & 1);
-                const float l = sStat[t * 128 + r];
+                float l = sStat[t * 128 + r];
                 const float m = sStat[256 + t * 128 + r];
                 mbar_arrive(bar(B_STEMPTY + t));
                 const uint32_t grow = wk.row0 + t * wk.drow + r;
                 const bool row_ok = grow < p.Sq;
                 const size_t orow = (size_t)(wk.bh + t * wk.dbh) * p.Sq + grow;
                 uint8_t* optr = reinterpret_cast<uint8_t*>(p.o) + orow * (size_t)(p.D_real * 2);
-                const float inv = (l > 0.f) ? 1.f / l : 0.f;        // rows without a visible key: O = 0, LSE = -inf
                 mbar_wait(bar(B_OFULL + t), it & 1);
                 tc_fence_after();
+                if constexpr (C::ROWSUM_MMA) {                        // row sum = column D of O (sum of the P values the MMA actually used)
+                    uint32_t ls[16];
+                    tmem_ld16(tO + D, ls);
+                    tmem_wait_ld();
+                    l = (m == -INFINITY) ? 0.f : __uint_as_float(ls[0]);
+                }
+                const float inv = (l > 0.f) ? 1.f / l : 0.f;        // rows without a visible key: O = 0, LSE = -inf
 #pragma unroll
                 for (int c = 0; c < D / 32; ++c) {
                     uint32_t o[32];
@@ -584,7 +608,9 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     uint32_t& gpv = t ? gpv1 : gpv0;
                     const uint32_t n = t ? c.n1 : c.n0;
                     const bool first = c.j == 0, last = c.j == n - 1;
-                    const uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
+                    uint32_t b_lo = HI_V_LO | ((sb + C::OFF_KV + vstage * C::TILE_BYTES) >> 4);
+                    if constexpr (C::ROWSUM_MMA)                         // columns [64,80) of "V" come from the ones tile: LBO = its distance from this stage
+                        b_lo = (b_lo & ~(0x3FFFu << 16)) | ((((C::OFF_ONES - C::OFF_KV) - vstage * C::TILE_BYTES) >> 4) << 16);
                     const uint32_t a = tmem + (t ? C::COL_P1 : C::COL_P0);
                     const uint32_t d = tmem + (t ? C::COL_O1 : C::COL_O0);
                     tr.ev(1 + 16 * t, gpv);

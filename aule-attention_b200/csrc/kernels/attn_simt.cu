@@ -228,8 +228,8 @@ __device__ void bwd_dq_body(const SimtParams& p) {
         for (int j = 0; j < TILE; ++j) {
             const float s = lane8_sum(frag_dot(qf, sK[j], slice, ngroups)) * p.scale;
             const float dp = lane8_sum(frag_dot(dof, sV[j], slice, ngroups));
-            const bool vis = visible(row, kb + j, p.Sk, p.causal, -1) && row < p.Sq;
-            const float pj = vis ? expf(s - lse) : 0.f;            // P = exp(S - LSE)   (:321)
+            const bool vis = visible(row, kb + j, p.Sk, p.causal, p.window) && row < p.Sq;
+            const float pj = vis ? expf(s - lse) : 0.f;            // P = exp(S - LSE)   (:321); a row without a visible key never gets here
             const float ds = pj * (dp - dlt) * p.scale;            // dS = P o (dP - Delta) * scale (:330)
             frag_axpy(acc, ds, sK[j], slice, ngroups);             // dQ += dS K (:336)
         }
@@ -281,7 +281,7 @@ __device__ void bwd_dkv_body(const SimtParams& p) {
             for (int i = 0; i < TILE; ++i) {
                 const float s = lane8_sum(frag_dot(kf, sQ[i], slice, ngroups)) * p.scale;
                 const float dp = lane8_sum(frag_dot(vf, sDO[i], slice, ngroups));
-                const bool vis = (qb + i < p.Sq) && visible(qb + i, key, p.Sk, p.causal, -1);
+                const bool vis = (qb + i < p.Sq) && visible(qb + i, key, p.Sk, p.causal, p.window);
                 const float pj = vis ? expf(s - sLse[i]) : 0.f;
                 frag_axpy(dv, pj, sDO[i], slice, ngroups);                  // dV += P^T dO (:324)
                 const float ds = pj * (dp - sDelta[i]) * p.scale;

@@ -63,7 +63,13 @@ struct FwdCfg {
     static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
     static constexpr uint32_t OFF_Q = 0;
     static constexpr uint32_t OFF_KV = OFF_Q + NQ * TILE_BYTES;
-    static constexpr uint32_t OFF_STAT = OFF_KV + NS * TILE_BYTES; // float l[2][128], m[2][128]
+    // D = 64 only: the softmax row sums come out of the P V MMA itself.  A constant [128 keys][64] tile whose column 0 is 1.0
+    // sits behind the K/V ring; the V descriptor's leading-dimension offset points the MMA's columns [64,80) at it, so
+    // O gets a 65th column = sum_j P_ij -- the 64 FADD2 per row and block leave the (issue-bound) softmax warps, the
+    // tensor pipe (half idle at D = 64) pays 25 % more P V work.  D = 128 has no TMEM columns left for it.
+    static constexpr bool ROWSUM_MMA = (D == 64);
+    static constexpr uint32_t OFF_ONES = OFF_KV + NS * TILE_BYTES;
+    static constexpr uint32_t OFF_STAT = OFF_ONES + (ROWSUM_MMA ? CHUNK_BYTES : 0); // float l[2][128], m[2][128]
     static constexpr uint32_t OFF_WORK = OFF_STAT + 4 * 128 * 4;   // 8 work descriptors x 32 B
     static constexpr uint32_t OFF_BAR = OFF_WORK + 8 * 32;
     static constexpr int NBAR = 39 + 2 * NS;
@@ -71,7 +77,8 @@ struct FwdCfg {
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
     // TMEM columns (512 allocated)
-    static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 192, COL_O0 = 256, COL_O1 = 256 + D;
+    static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 192, COL_O0 = 256, COL_O1 = ROWSUM_MMA ? 384 : 256 + D;
+    static constexpr uint32_t PV_N = ROWSUM_MMA ? D + 16 : D;     // columns of the P V MMA (row sum in column D)
     // register budget per thread after setmaxnreg (512 threads x 128 at launch = 64 K registers):
     // 2 softmax warpgroups x 184 + epilogue warpgroup x 64 + issuer/producer warpgroup x 80 = 512 x 128
     static constexpr int REGS_SOFTMAX = 184, REGS_EPILOGUE = 64, REGS_OTHER = 80;

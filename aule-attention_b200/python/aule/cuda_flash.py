@@ -50,9 +50,6 @@ class FlashAttentionCudaFunc(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
-        if ctx.window_size is not None and ctx.window_size > 0:
-            raise ffi.AuleError("backward with a sliding window is not supported "
-                                "(the reference's backward ignores the window, triton_flash.py:313-319)")
         lib = ffi.ensure_init()
         B, Hq, Sq, D = q.shape
         _, Hkv, Sk, _ = k.shape
@@ -60,10 +57,18 @@ class FlashAttentionCudaFunc(torch.autograd.Function):
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         dev = q.device.index
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.aule_attention_backward_dptr(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
-                                              lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                              B, Hq, Hkv, Sq, Sk, D, _TORCH_TO_AULE[ctx.cdt], ctx.scale,
-                                              1 if ctx.causal else 0, dev, stream)
+        window = int(ctx.window_size) if ctx.window_size is not None and ctx.window_size > 0 else -1
+        if window > 0:
+            # the window is part of the mask in the backward too (the reference's backward forgets it, triton_flash.py:313-319)
+            rc = lib.aule_attention_backward_window_dptr(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                                                         lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                         B, Hq, Hkv, Sq, Sk, D, _TORCH_TO_AULE[ctx.cdt], ctx.scale,
+                                                         1 if ctx.causal else 0, window, dev, stream)
+        else:
+            rc = lib.aule_attention_backward_dptr(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                                                  lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                  B, Hq, Hkv, Sq, Sk, D, _TORCH_TO_AULE[ctx.cdt], ctx.scale,
+                                                  1 if ctx.causal else 0, dev, stream)
         _check(rc, "Backward pass failed")
         od = ctx.orig_dtype
         return dq.to(od), dk.to(od), dv.to(od), None, None, None         # :526

@@ -69,6 +69,7 @@ def _proto(lib):
         "aule_attention_forward_gravity": ([u64] * 7 + [i32, u32, i32], i32),
         "aule_attention_forward_dptr": ([u64] * 5 + [u32] * 6 + [i32, c.c_float, i32, i32, i32, u64], i32),
         "aule_attention_backward_dptr": ([u64] * 9 + [u32] * 6 + [i32, c.c_float, i32, i32, u64], i32),
+        "aule_attention_backward_window_dptr": ([u64] * 9 + [u32] * 6 + [i32, c.c_float, i32, i32, i32, u64], i32),
         "aule_attention_forward_host": ([vp, vp, vp, vp, fp] + [u32] * 6 + [i32, c.c_float, i32, i32, i32], i32),
         "aule_attention_backward_host": ([vp] * 5 + [fp] + [vp] * 3 + [u32] * 6 + [i32, c.c_float, i32, i32], i32),
         "aule_rope_dptr": ([u64] * 4 + [u32] * 5 + [i32, i32, i32, i32, u64], i32),

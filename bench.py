@@ -231,9 +231,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; stdout is ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout is ONE JSON line: the image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner on stdout (so does
+        # WARN).  Drop the banner-only level and send whatever NCCL still logs (a level the caller chose) to stderr.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         cpu_group = dist.new_group(backend="gloo")     # host-side barrier for the single-process spanning section

@@ -160,6 +160,16 @@ AULE_API int32_t aule_attention_backward_dptr(uint64_t q, uint64_t k, uint64_t v
                                               float scale, int32_t causal, int32_t device,
                                               uint64_t cu_stream);
 
+/* Backward of a forward that used a sliding window (same `window` meaning as aule_attention_forward_dptr).  The
+ * reference's backward ignores the window (triton_flash.py:313-319: window_size is never saved), which makes its gradients
+ * wrong for windowed attention; here the mask is applied.  Runs the deterministic CUDA-core kernels (the tensor-core
+ * backward covers causal / full masks); window <= 0 is aule_attention_backward_dptr. */
+AULE_API int32_t aule_attention_backward_window_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o, uint64_t d_o,
+                                                     uint64_t lse, uint64_t dq, uint64_t dk, uint64_t dv, uint32_t B,
+                                                     uint32_t Hq, uint32_t Hkv, uint32_t Sq, uint32_t Sk, uint32_t D,
+                                                     int32_t dtype, float scale, int32_t causal, int32_t window,
+                                                     int32_t device, uint64_t cu_stream);
+
 /* Host-buffer forward for any dtype: stages through device memory with the
  * H2D copy of batch b+1 / D2H copy of batch b-1 overlapped with the kernel of
  * batch b (3 streams).  Page-locked caller buffers are copied directly; pageable ones (NumPy arrays) go through the

@@ -136,7 +136,7 @@ def attention_rows(q, k, v, b, h, row0, nrows, causal=True, scale=None, acc=np.f
     return (p / l) @ va, (smax + np.log(l))[:, 0]
 
 
-def attention_bwd_ref(q, k, v, do, causal=True, scale=None, acc=np.float64):
+def attention_bwd_ref(q, k, v, do, causal=True, scale=None, acc=np.float64, window=-1):
     """Analytic gradients (triton_flash.py:321-347, attention_backward_f32.comp:142-222):
         P = exp(S - LSE); Delta_i = sum_d O_id dO_id; dV = P^T dO; dP = dO V^T;
         dS = P o (dP - Delta) * scale; dQ = dS K; dK = dS^T Q;
@@ -151,15 +151,17 @@ def attention_bwd_ref(q, k, v, do, causal=True, scale=None, acc=np.float64):
     va = _expand_kv(v, Hq).astype(acc)
     doa = do.astype(acc)
     s = np.einsum('bhqd,bhkd->bhqk', qa, ka, optimize=True) * acc(scale)
-    m = _mask(Sq, Sk, causal, -1)
+    m = _mask(Sq, Sk, causal, window)
     if m.any():
         s = np.where(m, -np.inf, s)
     smax = s.max(axis=-1, keepdims=True)
-    e = np.exp(s - smax)
-    l = e.sum(axis=-1, keepdims=True)
-    p = e / l
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.exp(s - np.where(np.isfinite(smax), smax, 0.0))
+        l = e.sum(axis=-1, keepdims=True)
+        p = np.where(l > 0, e / np.where(l > 0, l, 1.0), 0.0)     # rows without a visible key contribute nothing
     o = np.einsum('bhqk,bhkd->bhqd', p, va, optimize=True)
-    lse = (smax + np.log(l))[..., 0]
+    with np.errstate(divide="ignore"):
+        lse = (smax + np.log(l))[..., 0]
     delta = (o * doa).sum(axis=-1, keepdims=True)
     dv_full = np.einsum('bhqk,bhqd->bhkd', p, doa, optimize=True)
     dp = np.einsum('bhqd,bhkd->bhqk', doa, va, optimize=True)

@@ -113,6 +113,28 @@ def test_rows_without_visible_key_agree_across_kernels(aule):
     assert orc.rel_err_to_scale(out[:, :, ~dead], out32[:, :, ~dead]) <= BF16_TOL
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("causal,window", [(True, 24), (True, 200), (False, 50)])
+def test_sliding_window_backward(aule, dtype, causal, window):
+    """backward with a window used to raise.  The reference's own backward ignores the window
+    (triton_flash.py:313-319), so the expected values are the oracle's analytic gradients with the mask applied."""
+    import torch
+    td = {"bf16": torch.bfloat16, "f32": torch.float32}[dtype]
+    torch.manual_seed(4)
+    q = torch.randn(1, 4, 300, 64, device="cuda").to(td).requires_grad_()
+    k = torch.randn(1, 2, 300, 64, device="cuda").to(td).requires_grad_()
+    v = torch.randn(1, 2, 300, 64, device="cuda").to(td).requires_grad_()
+    out = aule.flash_attention(q, k, v, causal=causal, window_size=window)
+    do = torch.randn_like(out)
+    out.backward(do)
+    rq, rk, rv, rdo = (t.detach().float().cpu().numpy() for t in (q, k, v, do))
+    dq, dk, dv, o, _ = orc.attention_bwd_ref(rq, rk, rv, rdo, causal=causal, window=window)
+    tol = BF16_TOL if dtype == "bf16" else FP32_TOL
+    assert orc.rel_err_to_scale(out.detach().float().cpu().numpy(), o) <= tol
+    for g_, e_ in ((q.grad, dq), (k.grad, dk), (v.grad, dv)):
+        assert orc.rel_err_to_scale(g_.float().cpu().numpy(), e_) <= tol
+
+
 # ------------------------------------------------------------------ RoPE
 @pytest.mark.parametrize("case", ["rope_gqa_1x4x64x64", "rope_mha_1x2x48x128"])
 def test_rope_vs_reference_golden(aule, golden_r2, case):
@@ -235,7 +257,7 @@ def test_config_c_samples_elementwise(aule):
         ks, vs = (t[b, hk].float().cpu().numpy()[None, None] for t in (k, v))
         exp, exp_lse = orc.attention_rows(qs, ks, vs, 0, 0, r0, 128, causal=True)
         got = out[b, h, r0:r0 + 128].float().cpu().numpy()
-        ok, nbad, worst_abs, worst_rel = orc.allclose_zig(got, exp, atol=2e-3, rtol=1e-2)
+        ok, nbad, worst_abs, worst_rel = orc.allclose_zig(got, exp, atol=1e-2, rtol=1e-2)   # bf16 output: half an ulp at |o| in [2,4) is 7.8e-3
         assert ok, (b, h, r0, nbad, worst_abs, worst_rel)
         np.testing.assert_allclose(lse[b, h, r0:r0 + 128].cpu().numpy(), exp_lse, rtol=2e-3, atol=2e-3)
 

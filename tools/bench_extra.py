@@ -29,6 +29,49 @@ def timeit(fn, steps=10, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
+_REF_SCRIPT = r"""
+import json, sys, torch
+sys.path.insert(0, sys.argv[1])
+import aule                                       # the REFERENCE package (baseline/_ref), unmodified
+from aule.triton_flash import flash_attention_triton
+B, Hq, Hkv, S, D = (int(x) for x in sys.argv[2:7])
+g = torch.Generator(device="cuda").manual_seed(1)
+q = torch.randn(B, Hq, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
+k = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
+v = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
+with torch.no_grad():
+    for _ in range(3):
+        flash_attention_triton(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        flash_attention_triton(q, k, v, causal=True)
+    e1.record()
+    torch.cuda.synchronize()
+print("MS", e0.elapsed_time(e1) / 5)
+"""
+
+
+def reference_triton(B, Hq, Hkv, S, D, flops):
+    """The reference's own GPU path (python/aule/triton_flash.py:529 flash_attention_triton), recompiled by Triton for this
+    GPU, as the yardstick BASELINE.md 4 / SURVEY 2.3 ask for.  Needs the pip-installed reference under baseline/_ref."""
+    import subprocess
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "aule")):
+        return "unavailable: baseline/_ref not installed"
+    try:
+        env = dict(os.environ); env.pop("PYTHONPATH", None)
+        p = subprocess.run([sys.executable, "-c", _REF_SCRIPT, ref, str(B), str(Hq), str(Hkv), str(S), str(D)],
+                           capture_output=True, text=True, timeout=900, env=env)
+        ms = [float(ln.split()[1]) for ln in p.stdout.splitlines() if ln.startswith("MS ")]
+        if not ms:
+            return "failed: " + (p.stderr.strip().splitlines() or ["no output"])[-1][:200]
+        return flops / ms[-1] / 1e9
+    except Exception as e:
+        return f"failed: {type(e).__name__}"
+
+
 def run(name, B, Hq, Hkv, S, D, dtype=torch.bfloat16, bwd=False, yard=True):
     g = torch.Generator(device="cuda").manual_seed(1)
     q = torch.randn(B, Hq, S, D, device="cuda", dtype=dtype, generator=g)
@@ -61,6 +104,7 @@ def run(name, B, Hq, Hkv, S, D, dtype=torch.bfloat16, bwd=False, yard=True):
             res["torch_sdpa_fwd_tflops"] = fl / t / 1e9
         except Exception as e:
             res["torch_sdpa_fwd_tflops"] = f"unavailable: {type(e).__name__}"
+        res["reference_triton_fwd_tflops"] = reference_triton(B, Hq, Hkv, S, D, fl)
         try:
             from flash_attn import flash_attn_func
             qf, kf, vf = (x.transpose(1, 2).contiguous() for x in (q, k, v))
