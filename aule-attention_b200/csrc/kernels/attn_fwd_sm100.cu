@@ -801,4 +801,7 @@ AULE_FWD_VARIANT(9, 1, 4, false, 256 + 1 + 32768)
 AULE_FWD_VARIANT(10, 1, 4, false, 256 + 1 + 4096)
 AULE_FWD_VARIANT(11, 0, 4, false, 256 + 1)
 AULE_FWD_VARIANT(12, 1, 4, false, 256 + 1 + 65536)
+AULE_FWD_VARIANT(13, 1, 4, false, 2 + 131072)          // one P publish per block
+AULE_FWD_VARIANT(14, 1, 4, false, 256 + 2 + 131072)
+AULE_FWD_VARIANT(15, 1, 4, false, 2 + 4 + 131072)
 #endif
