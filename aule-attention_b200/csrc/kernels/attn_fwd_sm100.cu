@@ -188,6 +188,11 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
     const uint32_t wring = sb + C::OFF_WORK;
 
     if (threadIdx.x == 0 && (sb & 1023u)) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
+    // VAR bit 524288: one mbarrier arrival per WARP (after __syncwarp) instead of one per thread.  An arrive from 32 lanes on
+    // one address is 32 serialised shared-memory atomics; ~24 such warp-arrives per block pair compete with the operand
+    // reads of the SS-form Q K^T MMAs, which need the full 128 B/clk of shared-memory bandwidth on their own.
+    constexpr bool WARP_ARR = (VAR & 524288) != 0;
+    constexpr uint32_t NARR = WARP_ARR ? 4 : 128;                   // arrivals of one 128-thread group
 
     if (warp == 13 && lane == 0) {
         for (int i = 0; i < 3; ++i) {
@@ -196,18 +201,18 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar(B_SFULL + t), 1);     // tcgen05.commit
-            mbar_init(bar(B_PFULL + t), 128);   // softmax threads
-            mbar_init(bar(B_PFULLB + t), 128);  // softmax threads
+            mbar_init(bar(B_PFULL + t), NARR);  // softmax threads
+            mbar_init(bar(B_PFULLB + t), NARR); // softmax threads
             mbar_init(bar(B_PVDONE + t), 1);    // tcgen05.commit
             mbar_init(bar(B_OFULL + t), 1);     // tcgen05.commit
-            mbar_init(bar(B_OEMPTY + t), 128);  // epilogue threads
-            mbar_init(bar(B_STFULL + t), 128);  // softmax threads
-            mbar_init(bar(B_STEMPTY + t), 128); // epilogue threads
+            mbar_init(bar(B_OEMPTY + t), NARR); // epilogue threads
+            mbar_init(bar(B_STFULL + t), NARR); // softmax threads
+            mbar_init(bar(B_STEMPTY + t), NARR);// epilogue threads
         }
-        mbar_init(bar(B_SFREE), 128);           // softmax threads of whichever tile owns S
+        mbar_init(bar(B_SFREE), NARR);          // softmax threads of whichever tile owns S
         for (int i = 0; i < WK_SLOTS; ++i) {
             mbar_init(bar(B_WKFULL + i), 1);     // scheduler (TMA thread)
-            mbar_init(bar(B_WKEMPTY + i), 385);  // 1 MMA + 256 softmax + 128 epilogue threads
+            mbar_init(bar(B_WKEMPTY + i), 1 + 3 * NARR);  // 1 MMA + 256 softmax + 128 epilogue threads
         }
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar(B_KVFULL + s), 1);
@@ -251,7 +256,12 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         uint32_t g = 0, it = 0;                                     // g: blocks processed so far by this tile
         Work wk;
         auto WAIT = [&](uint32_t b, uint32_t parity) { if constexpr (!SO) mbar_wait<HOT_HINT>(b, parity); };
-        auto ARRIVE = [&](uint32_t b) { if constexpr (!SO) mbar_arrive(b); };
+        auto ARRIVE = [&](uint32_t b) {
+            if constexpr (!SO) {
+                if constexpr (WARP_ARR) { __syncwarp(); if (lane == 0) mbar_arrive(b); }
+                else mbar_arrive(b);
+            }
+        };
         if constexpr (SO) {                                         // benign scores: S = 0 everywhere
             uint32_t z[32];
 #pragma unroll
@@ -497,13 +507,17 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
         uint32_t it = 0;
         Work wk;
         for (; fetch_work(bar(B_WKFULL), wring, it, wk); ++it) {
-            mbar_arrive(bar(B_WKEMPTY + (it & (WK_SLOTS - 1))));
+            auto ARRIVE = [&](uint32_t b) {
+                if constexpr (WARP_ARR) { __syncwarp(); if (lane == 0) mbar_arrive(b); }
+                else mbar_arrive(b);
+            };
+            ARRIVE(bar(B_WKEMPTY + (it & (WK_SLOTS - 1))));
             for (uint32_t t = 0; t < 2; ++t) {
                 const uint32_t tO = tmem + lane_addr + (t ? C::COL_O1 : C::COL_O0);
                 mbar_wait(bar(B_STFULL + t), it & 1);
                 float l = sStat[t * 128 + r];
                 const float m = sStat[256 + t * 128 + r];
-                mbar_arrive(bar(B_STEMPTY + t));
+                ARRIVE(bar(B_STEMPTY + t));
                 const uint32_t grow = wk.row0 + t * wk.drow + r;
                 const bool row_ok = grow < p.Sq;
                 const size_t orow = (size_t)(wk.bh + t * wk.dbh) * p.Sq + grow;
@@ -524,7 +538,7 @@ __device__ __forceinline__ void fwd_body(const CUtensorMap* tmQ, const CUtensorM
                     tmem_wait_ld();
                     if (c == D / 32 - 1) {                          // O_t fully read: MMA may overwrite it
                         tc_fence_before();
-                        mbar_arrive(bar(B_OEMPTY + t));
+                        ARRIVE(bar(B_OEMPTY + t));
                     }
                     // 32 fp32 -> 32 x 16-bit = 64 B of this row
                     uint32_t v[16];
@@ -801,7 +815,7 @@ AULE_FWD_VARIANT(9, 1, 4, false, 256 + 1 + 32768)
 AULE_FWD_VARIANT(10, 1, 4, false, 256 + 1 + 4096)
 AULE_FWD_VARIANT(11, 0, 4, false, 256 + 1)
 AULE_FWD_VARIANT(12, 1, 4, false, 256 + 1 + 65536)
-AULE_FWD_VARIANT(13, 1, 4, false, 2 + 131072)          // one P publish per block
-AULE_FWD_VARIANT(14, 1, 4, false, 256 + 2 + 131072)
-AULE_FWD_VARIANT(15, 1, 4, false, 2 + 4 + 131072)
+AULE_FWD_VARIANT(13, 1, 4, false, AULE_FWD_VAR + 524288)   // one mbarrier arrival per warp
+AULE_FWD_VARIANT(14, 1, 4, true, AULE_FWD_VAR + 524288)
+AULE_FWD_VARIANT(15, 1, 8, false, AULE_FWD_VAR + 524288)
 #endif

@@ -15,7 +15,7 @@ pub const AttentionPushConstants = extern struct {
     head_dim: u32,
     scale: f32, // <= 0 => 1/sqrt(head_dim), computed in the engine like attention_pipeline.zig:329
     causal: u32,
-    has_rope: u32 = 0, // RoPE prologue is outside the B200 hot path
+    has_rope: u32 = 0, // RoPE is a prologue launch of the C side (aule_attention_forward_rope_dptr), not a push constant
     num_kv_heads: u32,
     key_seq_len: u32,
     window_size: i32 = -1,

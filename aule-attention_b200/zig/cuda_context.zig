@@ -30,7 +30,9 @@ pub const c = struct {
     pub extern "c" fn aule_attention_backward_dptr(q: u64, k: u64, v: u64, o: u64, d_o: u64, lse: u64, dq: u64, dk: u64, dv: u64, B: u32, Hq: u32, Hkv: u32, Sq: u32, Sk: u32, D: u32, dtype: i32, scale: f32, causal: i32, device: i32, cu_stream: u64) i32;
     pub extern "c" fn aule_attention_forward_paged(q: u64, k: u64, v: u64, o: u64, rot_cos: u64, rot_sin: u64, causal: i32, window: i32) i32;
     pub extern "c" fn aule_attention_paged_decode_dptr(q: u64, k_cache: u64, v_cache: u64, block_tables: u64, context_lens: u64, out: u64, B: u32, Hq: u32, Hkv: u32, D: u32, num_blocks: u32, block_size: u32, max_blocks_per_seq: u32, max_context_len: u32, dtype: i32, scale: f32, window: i32, device: i32, cu_stream: u64) i32;
-    pub extern "c" fn aule_rope_dptr(x: u64, out: u64, cos: u64, sin: u64, B: u32, H: u32, S: u32, D: u32, dtype: i32, inverse: i32, device: i32, cu_stream: u64) i32;
+    pub extern "c" fn aule_rope_dptr(x: u64, out: u64, cos: u64, sin: u64, B: u32, H: u32, S: u32, D: u32, table_rows: u32, interleaved: i32, dtype: i32, inverse: i32, device: i32, cu_stream: u64) i32;
+    pub extern "c" fn aule_attention_forward_rope_dptr(q: u64, k: u64, v: u64, o: u64, lse_or_0: u64, cos: u64, sin: u64, table_rows: u32, interleaved: i32, B: u32, Hq: u32, Hkv: u32, Sq: u32, Sk: u32, D: u32, dtype: i32, scale: f32, causal: i32, window: i32, device: i32, cu_stream: u64) i32;
+    pub extern "c" fn aule_attention_forward_spanning_dptr(q: u64, k: u64, v: u64, o: u64, lse_or_0: u64, B: u32, Hq: u32, Hkv: u32, Sq: u32, Sk: u32, D: u32, dtype: i32, scale: f32, causal: i32, window: i32, src_device: i32, cu_stream: u64, devices: [*]const i32, num_devices: i32, chunks: i32, timings_ms_or_null: ?[*]f32) i32;
     pub extern "c" fn aule_smoke_multiply(in: [*]const f32, out: [*]f32, n: u32) i32;
 };
 
