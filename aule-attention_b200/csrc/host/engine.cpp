@@ -118,15 +118,14 @@ std::string Engine::load_device(int ordinal) {
                                               (int)FwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem d128)");
     }
     for (int t = 1; t < 3 && e.empty(); ++t) {
-        e = get(&d.bwd_sm100[t][0], std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + "_d64");
-        if (e.empty()) e = get(&d.bwd_sm100[t][1], std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + "_d128");
-        if (e.empty()) e = get(&d.bwd_delta[t], std::string("aule_bwd_delta_") + kDtypeSuffix[t]);
-        if (e.empty())
-            e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                              (int)BwdCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d64)");
-        if (e.empty())
-            e = check(drv_.cuFuncSetAttribute(d.bwd_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                              (int)BwdCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd d128)");
+        // v3 dK/dV kernel: tuning builds only (optional symbols)
+        for (int dd = 0; dd < 2; ++dd) {
+            const std::string nm = std::string("aule_bwd_sm100_") + kDtypeSuffix[t] + (dd ? "_d128" : "_d64");
+            if (drv_.cuModuleGetFunction(&d.bwd_sm100[t][dd], d.mod, nm.c_str()) != CUDA_SUCCESS) { d.bwd_sm100[t][dd] = nullptr; continue; }
+            drv_.cuFuncSetAttribute(d.bwd_sm100[t][dd], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                    dd ? (int)BwdCfg<128>::SMEM_BYTES : (int)BwdCfg<64>::SMEM_BYTES);
+        }
+        e = get(&d.bwd_delta[t], std::string("aule_bwd_delta_") + kDtypeSuffix[t]);
         if (e.empty()) e = get(&d.bwd_dkvt_sm100[t][0], std::string("aule_bwd_dkvt_sm100_") + kDtypeSuffix[t] + "_d64");
         if (e.empty()) e = get(&d.bwd_dkvt_sm100[t][1], std::string("aule_bwd_dkvt_sm100_") + kDtypeSuffix[t] + "_d128");
         if (e.empty())
@@ -452,6 +451,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             if (e.empty() && bwd_order_ != 2) {                 // (timing hook: 2 = dQ kernel only)
                 void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
                 if (bwd_serial_ & 2) {      // A/B hook (path bit 13): the v3 dK/dV kernel (P, dS staged through shared memory)
+                    if (!d.bwd_sm100[dtype][d128 ? 1 : 0]) { drv_.cuMemFreeAsync(delta, stream); return "the v3 dK/dV kernel is only present in tuning builds"; }
                     snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
                     e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, (unsigned)BwdCfg<128>::THREADS,
                                d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
@@ -877,7 +877,12 @@ std::string Engine::forward_spanning(int src_dev, CUstream stream, CUdeviceptr q
         if (lse && !(e = ensure_stage(d, 4, lse_unit * nu)).empty()) break;
         e = check(drv_.cuStreamWaitEvent(d.s_in, ev_ready, 0), "cuStreamWaitEvent");
         if (e.empty()) e = check(drv_.cuEventRecord(evs[i].ev[0], d.s_in), "cuEventRecord");
-        const uint32_t nch = std::min<uint32_t>((uint32_t)chunks, nu), per = (nu + nch - 1) / nch;
+        // A chunk is a kernel launch of its own: it must still fill the GPU.  Keep at least ~4 work items per SM in a chunk
+        // (config D at 8 GPUs: 4 heads per peer, 128 items of up to 256 blocks each per head -- one head per launch ran
+        // 1.65 ms against 0.81 ms for the four heads in one launch), however many chunks the caller asked for.
+        const uint64_t items_per_unit = (uint64_t)((s.Sq + 255) / 256) * group;
+        const uint32_t by_work = (uint32_t)std::max<uint64_t>(1, (uint64_t)nu * items_per_unit / (4ull * (uint64_t)d.sm_count));
+        const uint32_t nch = std::min<uint32_t>(std::min<uint32_t>((uint32_t)chunks, by_work), nu), per = (nu + nch - 1) / nch;
         for (uint32_t c = 0; c < nch && e.empty(); ++c) {
             const uint32_t a = c * per;
             if (a >= nu) break;

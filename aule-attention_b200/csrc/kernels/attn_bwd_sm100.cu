@@ -1141,10 +1141,14 @@ AULE_BWD100_T(aule_bwd_dkvt_sm100_bf16_d128, 128, true)
 AULE_BWD100_T(aule_bwd_dkvt_sm100_bf16_d64, 64, true)
 AULE_BWD100_T(aule_bwd_dkvt_sm100_f16_d128, 128, false)
 AULE_BWD100_T(aule_bwd_dkvt_sm100_f16_d64, 64, false)
+#ifdef AULE_TUNING_VARIANTS
+// the superseded v3 dK/dV kernel (P, dS staged through shared memory): tuning builds only, for A/B runs and as an independent
+// data path in tests (aule_set_kernel_path bit 13)
 AULE_BWD100(aule_bwd_sm100_bf16_d128, 128, true)
 AULE_BWD100(aule_bwd_sm100_bf16_d64, 64, true)
 AULE_BWD100(aule_bwd_sm100_f16_d128, 128, false)
 AULE_BWD100(aule_bwd_sm100_f16_d64, 64, false)
+#endif
 AULE_BWD100_DQ(aule_bwd_dq_sm100_bf16_d128, 128, true)
 AULE_BWD100_DQ(aule_bwd_dq_sm100_bf16_d64, 64, true)
 AULE_BWD100_DQ(aule_bwd_dq_sm100_f16_d128, 128, false)

@@ -273,7 +273,12 @@ def test_backward_dkv_kernel_generations_agree(aule):
         lib.aule_set_kernel_path(path)
         try:
             tq, tk, tv = (t.clone().requires_grad_() for t in (q, k, v))
-            aule.flash_attention(tq, tk, tv, causal=True).backward(do)
+            try:
+                aule.flash_attention(tq, tk, tv, causal=True).backward(do)
+            except ffi.AuleError as ex:
+                if "tuning builds" in str(ex):
+                    pytest.skip("release build: the v3 kernel is compiled only with -DAULE_TUNING_VARIANTS")
+                raise
             torch.cuda.synchronize()
             grads.append((tq.grad.float(), tk.grad.float(), tv.grad.float()))
         finally:
