@@ -67,6 +67,11 @@ template <bool MASK, int EMU = 0>
 __device__ __forceinline__ void p_from_s(const uint32_t (&s)[32], float* pv, float c2, float lse2, uint32_t col0, uint32_t row,
                                          uint32_t Sk, bool row_ok, bool diag) {
     const float2 cc = make_float2(c2, c2), nl = make_float2(-lse2, -lse2);
+    uint32_t alive = 0xffffffffu;                         // bit e: column col0+e of this row is visible
+    if (MASK) {
+        const int64_t last = min((int64_t)Sk - 1, diag ? (int64_t)row : (int64_t)0x7fffffff) - (int64_t)col0;   // last visible local column
+        alive = !row_ok || last < 0 ? 0u : (last >= 31 ? 0xffffffffu : (0xffffffffu >> (31 - (int)last)));
+    }
 #if AULE_BWD_XPASS
     uint32_t xs[32];
 #pragma unroll
@@ -91,10 +96,9 @@ __device__ __forceinline__ void p_from_s(const uint32_t (&s)[32], float* pv, flo
             v.x = ex2(x.x);
             v.y = ex2(x.y);
         }
-        if (MASK) {
-            const uint32_t col = col0 + e;
-            v.x = (row_ok && col < Sk && !(diag && col > row)) ? v.x : 0.f;
-            v.y = (row_ok && col + 1 < Sk && !(diag && col + 1 > row)) ? v.y : 0.f;
+        if (MASK) {                                       // one alive-bit test + select per element (see attn_fwd_sm100.cu)
+            v.x = (alive & (1u << e)) ? v.x : 0.f;
+            v.y = (alive & (2u << e)) ? v.y : 0.f;
         }
         pv[e] = v.x;
         pv[e + 1] = v.y;
@@ -685,6 +689,13 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             const bool masked = diag || !key_ok || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
             if (++i == nqb) i = i_begin;
 
+            uint32_t alive = 0xffffffffu;
+            if (masked) {
+                const int64_t first = diag ? (int64_t)key - (int64_t)q0 : 0, last = (int64_t)p.Sq - 1 - (int64_t)q0;
+                const uint32_t lo_m = first <= 0 ? 0xffffffffu : (first > 31 ? 0u : (0xffffffffu << (int)first));
+                const uint32_t hi_m = last >= 31 ? 0xffffffffu : (last < 0 ? 0u : (0xffffffffu >> (31 - (int)last)));
+                alive = key_ok ? (lo_m & hi_m) : 0u;
+            }
             // ---- P phase: P^T = exp2(S^T*scale_log2 - lse2[query]) -> 16-bit, in place over the first 16 columns
             float pv[32];
             tr.ev(20, step);
@@ -728,12 +739,9 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                         v1.x = ex2(x1.x); v1.y = ex2(x1.y);
                         pv[4 * e4] = v0.x; pv[4 * e4 + 1] = v0.y; pv[4 * e4 + 2] = v1.x; pv[4 * e4 + 3] = v1.y;
                     }
-                    if (masked) {
+                    if (masked) {                                    // alive bits of this thread's 32 query columns: q >= key (diagonal), q < Sq
 #pragma unroll
-                        for (int e = 16 * half; e < 16 * half + 16; ++e) {
-                            const uint32_t q = q0 + e;
-                            pv[e] = (key_ok && q < p.Sq && !(diag && key > q)) ? pv[e] : 0.f;
-                        }
+                        for (int e = 16 * half; e < 16 * half + 16; ++e) pv[e] = (alive & (1u << e)) ? pv[e] : 0.f;
                     }
                     uint32_t pk[8];
 #pragma unroll
