@@ -143,6 +143,13 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.bwd_dq_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)aule_kp::BwdDqCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d128)");
     }
+    for (int t = 1; t < 3 && e.empty(); ++t) {
+        e = get(&d.bwd_fused_sm100[t], std::string("aule_bwd_fused_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty()) e = get(&d.bwd_dq_convert[t], std::string("aule_bwd_dq_convert_") + kDtypeSuffix[t]);
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_fused_sm100[t], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::BwdFCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd fused d128)");
+    }
     // tuning builds only: optional symbols
     for (int dd = 0; dd < 2; ++dd) {
         for (int v = 0; v < 16; ++v) {
@@ -445,9 +452,39 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             // config C/2 (gpurun s21) -- the heavy CTAs of later runs start late and the tail grows.
             bp.units_per_run = 0;
             bp.trace = (unsigned long long*)trace_;
+            bp.dq_acc = nullptr;
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
+            if (e.empty() && bwd_fused_ && d128 && bwd_order_ == 0) {
+                // Fused backward (attn_bwd_fused_sm100.cu): dK / dV as below, dQ reduced into an fp32 accumulator that is
+                // zeroed here and converted (x scale) afterwards.
+                const size_t n = (size_t)s.B * s.Hq * s.Sq * s.D;
+                CUdeviceptr acc = 0;
+                e = check(drv_.cuMemAllocAsync(&acc, n * sizeof(float), stream), "cuMemAllocAsync(dQ accumulator)");
+                if (e.empty()) e = check(drv_.cuMemsetD32Async(acc, 0, n, stream), "cuMemsetD32Async(dQ accumulator)");
+                bp.dq_acc = (float*)acc;
+                // CTA runs: the fp32 dQ rows a run reduces into (units x group x Sq x D x 4 bytes) should stay L2-resident
+                // while the run lasts, and the last run should be large enough that its heaviest CTAs do not make a tail.
+                bp.units_per_run = bwd_units_per_run_ ? (uint32_t)bwd_units_per_run_ : 8u;
+                if (e.empty()) {
+                    void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
+                    snprintf(name, sizeof(name), "aule_bwd_fused_sm100_%s_d128", kDtypeSuffix[dtype]);
+                    e = launch(d, d.bwd_fused_sm100[dtype], name, (unsigned)ctas, 1, 1, (unsigned)aule_kp::BwdFCfg<128>::THREADS,
+                               aule_kp::BwdFCfg<128>::SMEM_BYTES, stream, params);
+                }
+                if (e.empty()) {
+                    uint64_t n8 = n / 8;
+                    float sc = scale;
+                    void* params[] = {&acc, &dq, &n8, &sc};
+                    snprintf(name, sizeof(name), "aule_bwd_dq_convert_%s", kDtypeSuffix[dtype]);
+                    const unsigned blocks = (unsigned)std::min<uint64_t>((n8 + 255) / 256, (uint64_t)d.sm_count * 16);
+                    e = launch(d, d.bwd_dq_convert[dtype], name, blocks, 1, 1, 256, 0, stream, params);
+                }
+                if (acc) drv_.cuMemFreeAsync(acc, stream);
+                drv_.cuMemFreeAsync(delta, stream);
+                return e;
+            }
             if (e.empty() && bwd_order_ != 2) {                 // (timing hook: 2 = dQ kernel only)
                 void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
                 if (bwd_serial_ & 2) {      // A/B hook (path bit 13): the v3 dK/dV kernel (P, dS staged through shared memory)

@@ -7,4 +7,5 @@
 #include "attn_fwd_sm100_v4.cu"
 #endif
 #include "attn_bwd_sm100.cu"
+#include "attn_bwd_fused_sm100.cu"
 #include "attn_paged_sm100.cu"

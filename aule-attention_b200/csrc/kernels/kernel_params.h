@@ -120,6 +120,7 @@ struct BwdParams {
     int32_t causal;
     int32_t order;            // reserved for A/B tuning of the MMA issue order (unused by the shipped kernels)
     unsigned long long* trace; // bring-up: CTA 0 records (tag << 48 | clock64) events here (3 x 4096 entries) or nullptr
+    float* dq_acc;            // fused kernel: [B,Hq,Sq,D] fp32 dQ accumulator (zeroed by the host, converted by aule_bwd_dq_convert_*)
 };
 template <int D>
 struct BwdCfg {
@@ -157,6 +158,28 @@ struct BwdTCfg {
     static constexpr uint32_t OFF_STAT = (2 + NQ + NDO) * TILE_BYTES;
     static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 256 * 4;   // two statistics buffers (published one step ahead)
     static constexpr uint32_t BAR_BYTES = 160;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+};
+
+// Fused backward (one kernel: dK, dV accumulate in TMEM, dQ partials are reduced into an fp32 accumulator in global memory):
+// K_j | V_j | Q ring (2) | dO ring (2) | dS^T tile | column statistics (2 x [lse2 128 | delta 128]) | barriers.
+template <int D>
+struct BwdFCfg {
+    static_assert(D == 128, "the fused backward is written for head_dim 128");
+    static constexpr int THREADS = 544;
+    static constexpr int NQ = 2, NDO = 2;
+    static constexpr int CHUNKS = D / 64;
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_K = 0, OFF_V = TILE_BYTES;
+    static constexpr uint32_t OFF_Q = 2 * TILE_BYTES;
+    static constexpr uint32_t OFF_DO = (2 + NQ) * TILE_BYTES;
+    static constexpr uint32_t OFF_DS = (2 + NQ + NDO) * TILE_BYTES;       // dS^T [128 keys][128 queries] 16-bit, two swizzled chunks
+    static constexpr uint32_t OFF_STAT = OFF_DS + 2 * CHUNK_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 256 * 4;
+    static constexpr uint32_t BAR_BYTES = 192;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");

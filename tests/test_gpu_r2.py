@@ -135,6 +135,42 @@ def test_sliding_window_backward(aule, dtype, causal, window):
         assert orc.rel_err_to_scale(g_.float().cpu().numpy(), e_) <= tol
 
 
+# ------------------------------------------------------------------ fused backward (opt-in)
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,causal,dtype", [
+    (1, 2, 1, 256, 256, True, "bf16"), (2, 4, 2, 1000, 1000, True, "f16"), (1, 2, 1, 300, 520, False, "bf16"), (1, 8, 2, 1536, 1536, True, "bf16")])
+def test_fused_backward_kernel_vs_oracle(aule, B, Hq, Hkv, Sq, Sk, causal, dtype):
+    """aule_set_kernel_path bit 17: ONE backward kernel (attn_bwd_fused_sm100.cu) that reduces dQ partials into an fp32
+    accumulator with red.global.add, the way the reference does (tl.atomic_add, triton_flash.py:335-339).  dK / dV must be
+    bit-identical to the deterministic two-kernel backward (same operands, same accumulation order); dQ within the bf16 bar."""
+    import torch
+    from aule import cuda_flash, ffi
+    lib = ffi.ensure_init()
+    td = {"bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    code = {"bf16": ffi.DTYPE_BF16, "f16": ffi.DTYPE_F16}[dtype]
+    q, k, v = ref_inputs(B, Hq, Sq, 128, Hkv=Hkv, Sk=Sk)
+    tq, tk, tv = (torch.from_numpy(np.ascontiguousarray(x)).cuda().to(td) for x in (q, k, v))
+    o, lse = cuda_flash.forward_with_lse(tq, tk, tv, causal=causal)
+    do = torch.randn(o.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).to(td)
+    res = {}
+    try:
+        for path in (0, 1 << 17):
+            dq, dk, dv = (torch.full_like(t, float("nan")) for t in (tq, tk, tv))
+            lib.aule_set_kernel_path(path)
+            rc = lib.aule_attention_backward_dptr(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                                  dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, Hq, Hkv, Sq, Sk, 128, code, 0.0,
+                                                  1 if causal else 0, 0, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, ffi.last_error()
+            torch.cuda.synchronize()
+            res[path] = (dq, dk, dv, lib.aule_last_kernel().decode())
+    finally:
+        lib.aule_set_kernel_path(0)
+    assert res[0][3].startswith("aule_bwd_dq_sm100") and res[1 << 17][3].startswith("aule_bwd_dq_convert"), (res[0][3], res[1 << 17][3])
+    assert torch.equal(res[0][1], res[1 << 17][1]) and torch.equal(res[0][2], res[1 << 17][2])
+    edq, edk, edv, _, _ = orc.attention_bwd_ref(*(t.float().cpu().numpy() for t in (tq, tk, tv, do)), causal=causal)
+    for g_, e_ in zip(res[1 << 17][:3], (edq, edk, edv)):
+        assert orc.rel_err_to_scale(g_.float().cpu().numpy(), e_) <= BF16_TOL
+
+
 # ------------------------------------------------------------------ RoPE
 @pytest.mark.parametrize("case", ["rope_gqa_1x4x64x64", "rope_mha_1x2x48x128"])
 def test_rope_vs_reference_golden(aule, golden_r2, case):

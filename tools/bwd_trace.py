@@ -2,7 +2,7 @@
 through aule_set_trace_buffer; this prints, per step, the event times relative to the step's first event.
 The tracer is compiled in only with  make -C aule-attention_b200 EXTRA_NVFLAGS=-DAULE_BWD_TRACE=1  (rebuild without it
 afterwards: the checks cost instructions in issue-bound kernels).
-usage: python tools/bwd_trace.py [dq|dkv] [first_step] [last_step]"""
+usage: python tools/bwd_trace.py [dq|dkv|fused] [first_step] [last_step]"""
 import os
 import sys
 
@@ -34,7 +34,7 @@ def call():
 
 
 serial = len(sys.argv) > 4 and sys.argv[4] == "serial"
-lib.aule_set_kernel_path(((1 if which == "dkv" else 2) << 10) | ((1 << 12) if serial else 0))
+lib.aule_set_kernel_path((1 << 17) if which == "fused" else (((1 if which == "dkv" else 2) << 10) | ((1 << 12) if serial else 0)))
 for _ in range(3):
     call()
 torch.cuda.synchronize()
@@ -60,6 +60,11 @@ names = {16: "iss: dK(i-1) done -> load Q(i+1)", 17: "iss: wait P", 18: "iss: P 
          20: "cmp: wait S", 21: "cmp: S ok", 22: "cmp: S in regs", 23: "cmp: P done, wait dP", 24: "cmp: dP ok", 25: "cmp: dS math done",
          26: "cmp: dS cols free", 27: "cmp: dS stored", 30: "iss: dQ(j-1) DONE", 31: "iss: dP issued", 32: "iss: dP DONE",
          33: "iss: S(j+1) issued", 34: "iss: S(j+1) DONE"}
+if which == "fused":
+    names = {10: "iss: wait dS", 11: "iss: dS ok -> dQ^T, dK", 12: "iss: dO(s+1) ok", 13: "iss: P half0 ok -> dV even", 14: "iss: dQ drained -> dP(s+1)",
+             15: "iss: P half1 ok -> dV odd", 16: "iss: Q(s+2) ok -> S(s+2)",
+             20: "cmp: wait dP", 21: "cmp: dP ok", 22: "cmp: dS math done", 23: "cmp: dS stored+fenced", 24: "cmp: S(s+1) ok",
+             25: "cmp: P half0 published", 26: "cmp: dQ^T ok", 27: "cmp: drained"}
 for t, region, code, step in rows:
     if lo <= step <= hi:
         print(f"{t - t0:9d}  r{region} step {step:3d}  {code:3d} {names.get(code, '')}")
