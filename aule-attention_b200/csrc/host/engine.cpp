@@ -138,10 +138,16 @@ std::string Engine::load_device(int ordinal) {
         if (e.empty()) e = get(&d.bwd_dq_sm100[t][1], std::string("aule_bwd_dq_sm100_") + kDtypeSuffix[t] + "_d128");
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.bwd_dq_sm100[t][0], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                              (int)aule_kp::BwdDqCfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d64)");
+                                              (int)aule_kp::BwdDq2Cfg<64>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d64)");
         if (e.empty())
             e = check(drv_.cuFuncSetAttribute(d.bwd_dq_sm100[t][1], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                              (int)aule_kp::BwdDqCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d128)");
+                                              (int)aule_kp::BwdDq2Cfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd dq d128)");
+        for (int dd = 0; dd < 2; ++dd) {     // v1 dQ kernel: tuning builds only (optional symbols)
+            const std::string nm = std::string("aule_bwd_dq1_sm100_") + kDtypeSuffix[t] + (dd ? "_d128" : "_d64");
+            if (drv_.cuModuleGetFunction(&d.bwd_dq1_sm100[t][dd], d.mod, nm.c_str()) != CUDA_SUCCESS) { d.bwd_dq1_sm100[t][dd] = nullptr; continue; }
+            drv_.cuFuncSetAttribute(d.bwd_dq1_sm100[t][dd], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                    dd ? (int)aule_kp::BwdDqCfg<128>::SMEM_BYTES : (int)aule_kp::BwdDqCfg<64>::SMEM_BYTES);
+        }
     }
     for (int t = 1; t < 3 && e.empty(); ++t) {
         e = get(&d.bwd_fused_sm100[t], std::string("aule_bwd_fused_sm100_") + kDtypeSuffix[t] + "_d128");
@@ -413,17 +419,20 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     if (!(e = check(drv_.cuMemAllocAsync(&delta, dbytes, stream), "cuMemAllocAsync(delta)")).empty()) return e;
 
     if (window == 0) window = -1;
-    // Tensor-core backward: 16-bit, D in {64,128}, causal / full masks.  A sliding window (the reference's backward ignores
-    // it, triton_flash.py:313-319 -- its gradients are then wrong) and other head dims run the deterministic CUDA-core kernels.
-    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D == 64 || s.D == 128) && path_ != kForceCudaCore && window < 0 &&
-                    ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0;
+    // Tensor-core backward: 16-bit, any head_dim <= 128 that is a multiple of 8 (the kernels run at 64 / 128: the TMA boxes
+    // zero-fill the padding columns of Q, K, V, dO and clip them from dK, dV; the dQ kernel predicates its own loads and
+    // stores), causal / full masks.  A sliding window (the reference's backward ignores it, triton_flash.py:313-319 -- its
+    // gradients are then wrong), fp32 and head dims that are not a multiple of 8 run the deterministic CUDA-core kernels.
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D % 8 == 0) && path_ != kForceCudaCore && window < 0 &&
+                    ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0 && !(bwd_dq_v1_ && s.D != 64 && s.D != 128);
     if (!tc && log_enabled())
         fprintf(stderr, "[aule] backward [%u,%u(%u),%u/%u,%u] %s: CUDA-core kernels (%s)\n", s.B, s.Hq, s.Hkv, s.Sq, s.Sk, s.D,
-                kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : window > 0 ? "sliding window" : "head_dim not 64/128 or unaligned pointers");
+                kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : window > 0 ? "sliding window" : "head_dim % 8 != 0 or unaligned pointers");
     if (tc) {
         // Tensor-core backward: Delta pre-pass, then the dK/dV kernel (key block outer) and the dQ kernel (query block
         // outer).  No atomics and no workspace beyond Delta: bit-reproducible.
-        const bool d128 = s.D == 128;
+        const bool d128 = s.D > 64;                        // kernel (padded) head_dim 128, else 64
+        const uint32_t DP = d128 ? 128u : 64u;
         char name[64];
         {
             uint64_t rows = (uint64_t)s.B * s.Hq * s.Sq;
@@ -444,9 +453,9 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             if (e.empty()) e = make_tmap(&tmdV, dtype, dv, (uint64_t)s.B * s.Hkv, s.Sk, s.D);
             BwdParams bp;
             bp.dq_out = (void*)dq; bp.q = (const void*)q; bp.d_o = (const void*)d_o; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
-            bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk;
+            bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk; bp.D_real = s.D;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
-            bp.order = bwd_serial_;
+            bp.order = bwd_serial_ | (bwd_legacy_poll_ ? 4 : 0);
             // dK/dV CTA order: all units at once.  Launching the KV-block CTAs of a few (batch, kv-head) units together
             // (Q/dO L2-resident, BwdParams::units_per_run = ceil(SMs / KV blocks)) measured SLOWER: 1.36 vs 1.21 ms on
             // config C/2 (gpurun s21) -- the heavy CTAs of later runs start late and the tail grows.
@@ -456,7 +465,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
-            if (e.empty() && bwd_fused_ && d128 && bwd_order_ == 0) {
+            if (e.empty() && bwd_fused_ && s.D == 128 && bwd_order_ == 0) {
                 // Fused backward (attn_bwd_fused_sm100.cu): dK / dV as below, dQ reduced into an fp32 accumulator that is
                 // zeroed here and converted (x scale) afterwards.
                 const size_t n = (size_t)s.B * s.Hq * s.Sq * s.D;
@@ -489,11 +498,11 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
                 void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
                 if (bwd_serial_ & 2) {      // A/B hook (path bit 13): the v3 dK/dV kernel (P, dS staged through shared memory)
                     if (!d.bwd_sm100[dtype][d128 ? 1 : 0]) { drv_.cuMemFreeAsync(delta, stream); return "the v3 dK/dV kernel is only present in tuning builds"; }
-                    snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+                    snprintf(name, sizeof(name), "aule_bwd_sm100_%s_d%u", kDtypeSuffix[dtype], DP);
                     e = launch(d, d.bwd_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1, (unsigned)BwdCfg<128>::THREADS,
                                d128 ? BwdCfg<128>::SMEM_BYTES : BwdCfg<64>::SMEM_BYTES, stream, params);
                 } else {                    // v4: transposed score tiles, P^T / dS^T stay in TMEM
-                    snprintf(name, sizeof(name), "aule_bwd_dkvt_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
+                    snprintf(name, sizeof(name), "aule_bwd_dkvt_sm100_%s_d%u", kDtypeSuffix[dtype], DP);
                     e = launch(d, d.bwd_dkvt_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas, 1, 1,
                                (unsigned)aule_kp::BwdTCfg<128>::THREADS,
                                d128 ? aule_kp::BwdTCfg<128>::SMEM_BYTES : aule_kp::BwdTCfg<64>::SMEM_BYTES, stream, params);
@@ -509,12 +518,21 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
                     sq = d.s_aux;
                     e = check(drv_.cuStreamWaitEvent(sq, d.ev_fork, 0), "cuStreamWaitEvent");
                 }
-                void* params[] = {&tmK, &tmV, &bp};
-                snprintf(name, sizeof(name), "aule_bwd_dq_sm100_%s_d%u", kDtypeSuffix[dtype], s.D);
-                if (e.empty())
+                if (e.empty() && bwd_dq_v1_) {          // A/B hook (path bit 23): the v1 dQ kernel
+                    if (!d.bwd_dq1_sm100[dtype][d128 ? 1 : 0]) e = "the v1 dQ kernel is only present in tuning builds";
+                    void* params[] = {&tmK, &tmV, &bp};
+                    snprintf(name, sizeof(name), "aule_bwd_dq1_sm100_%s_d%u", kDtypeSuffix[dtype], DP);
+                    if (e.empty())
+                        e = launch(d, d.bwd_dq1_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas_dq, 1, 1,
+                                   (unsigned)aule_kp::BwdDqCfg<128>::THREADS,
+                                   d128 ? aule_kp::BwdDqCfg<128>::SMEM_BYTES : aule_kp::BwdDqCfg<64>::SMEM_BYTES, sq, params);
+                } else if (e.empty()) {
+                    void* params[] = {&tmK, &tmV, &tmdO, &bp};
+                    snprintf(name, sizeof(name), "aule_bwd_dq_sm100_%s_d%u", kDtypeSuffix[dtype], DP);
                     e = launch(d, d.bwd_dq_sm100[dtype][d128 ? 1 : 0], name, (unsigned)ctas_dq, 1, 1,
-                               (unsigned)aule_kp::BwdDqCfg<128>::THREADS,
-                               d128 ? aule_kp::BwdDqCfg<128>::SMEM_BYTES : aule_kp::BwdDqCfg<64>::SMEM_BYTES, sq, params);
+                               (unsigned)aule_kp::BwdDq2Cfg<128>::THREADS,
+                               d128 ? aule_kp::BwdDq2Cfg<128>::SMEM_BYTES : aule_kp::BwdDq2Cfg<64>::SMEM_BYTES, sq, params);
+                }
                 if (fork) {
                     if (e.empty()) e = check(drv_.cuEventRecord(d.ev_join, sq), "cuEventRecord");
                     if (e.empty()) e = check(drv_.cuStreamWaitEvent(stream, d.ev_join, 0), "cuStreamWaitEvent");

@@ -52,6 +52,7 @@ struct Device {
     CUfunction bwd_dkvt_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // transposed dK/dV kernel (v4)
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dq_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // dQ kernel [dtype][D==128]
+    CUfunction bwd_dq1_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // superseded v1 dQ kernel (tuning builds)
     CUfunction bwd_fused_sm100[3] = {nullptr, nullptr, nullptr};   // fused backward (D = 128) [dtype]
     CUfunction bwd_dq_convert[3] = {nullptr, nullptr, nullptr};    // its fp32 dQ accumulator -> 16-bit
     CUfunction rope[3] = {nullptr, nullptr, nullptr};
@@ -155,8 +156,10 @@ public:
     //   bit 15     forward v4: no cross-item prefetch of the next work item's first Q K^T
     //   bit 17     backward: fused kernel (dQ reduced into an fp32 accumulator; D = 128 only) -- see bwd_fused_ below
     //   bits 18-22 backward, fused kernel: (batch, kv-head) units per CTA run (0 = default)
+    //   bit 23     backward: the v1 dQ kernel (tuning builds only; an error otherwise)
+    //   bit 24     backward dK/dV kernel: try_wait side polls in the issuer's load pump (the pre-round-2 behaviour; A/B)
     void set_kernel_path(int32_t p) {
-        bwd_fused_ = (p >> 17) & 1; bwd_units_per_run_ = (p >> 18) & 31;
+        bwd_fused_ = (p >> 17) & 1; bwd_units_per_run_ = (p >> 18) & 31; bwd_dq_v1_ = (p >> 23) & 1; bwd_legacy_poll_ = (p >> 24) & 1;
         pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; bwd_two_streams_ = !(p & 65536); path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
@@ -187,6 +190,8 @@ private:
     int32_t fwd_v4_ = 0;
     bool bwd_two_streams_ = true;
     int32_t bwd_fused_ = 0;
+    int32_t bwd_dq_v1_ = 0;
+    int32_t bwd_legacy_poll_ = 0;
     int32_t bwd_units_per_run_ = 0;
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)

@@ -114,7 +114,7 @@ __device__ __forceinline__ void bwd_fused_body(const CUtensorMap* tmQ, const CUt
             uint32_t ql = 0, ql_st = 0, ql_use = 0, ql_g = 0, ql_i = i_begin;
             uint32_t dl = 0, dl_st = 0, dl_use = 0, dl_g = 0, dl_i = i_begin;
             auto pump = [&]() {
-                if (ql < nsteps && (ql_use == 0 || mbar_try_wait<0>(bar_qfree0 + 8 * ql_st, (ql_use - 1) & 1))) {
+                if (ql < nsteps && (ql_use == 0 || mbar_test(bar_qfree0 + 8 * ql_st, (ql_use - 1) & 1))) {
                     const uint32_t bar = bar_qfull0 + 8 * ql_st, dst = sQ0 + ql_st * C::TILE_BYTES;
                     mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
@@ -129,7 +129,7 @@ __device__ __forceinline__ void bwd_fused_body(const CUtensorMap* tmQ, const CUt
                             tma_prefetch_3d(tmQ, c * 64, (int32_t)(ql_i * 128), (int32_t)(b * p.Hq + hk * group + ql_g));
                     }
                 }
-                if (dl < nsteps && (dl_use == 0 || mbar_try_wait<0>(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
+                if (dl < nsteps && (dl_use == 0 || mbar_test(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
                     const uint32_t bar = bar_dofull0 + 8 * dl_st, dst = sdO0 + dl_st * C::TILE_BYTES;
                     mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll

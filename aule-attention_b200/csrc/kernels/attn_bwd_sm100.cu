@@ -534,8 +534,13 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             // (q-head of the group, query block) of the next Q / dO load, advanced without divisions
             uint32_t ql = 0, ql_st = 0, ql_use = 0, ql_g = 0, ql_i = i_begin;
             uint32_t dl = 0, dl_st = 0, dl_use = 0, dl_g = 0, dl_i = i_begin;
+            // side polls never suspend (mbarrier.test_wait): a try_wait on a stage that is not free yet sleeps for the hardware's
+            // time limit (~400 cycles measured) and delays the check of the barrier the issuer is actually waiting for
+            // (p.order bit 2 = the old try_wait polls, for A/B)
+            const bool legacy_poll = (p.order & 4) != 0;
+            auto poll = [&](uint32_t bar, uint32_t parity) { return legacy_poll ? mbar_try_wait<0>(bar, parity) : mbar_test(bar, parity); };
             auto pump = [&]() {
-                if (ql < nsteps && (ql_use == 0 || mbar_try_wait<0>(bar_qfree0 + 8 * ql_st, (ql_use - 1) & 1))) {
+                if (ql < nsteps && (ql_use == 0 || poll(bar_qfree0 + 8 * ql_st, (ql_use - 1) & 1))) {
                     const uint32_t bar = bar_qfull0 + 8 * ql_st, dst = sQ0 + ql_st * C::TILE_BYTES;
                     mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
@@ -545,7 +550,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     if (++ql_i == nqb) { ql_i = i_begin; ++ql_g; }
                     if (++ql_st == NQ) { ql_st = 0; ++ql_use; }
                 }
-                if (dl < nsteps && (dl_use == 0 || mbar_try_wait<0>(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
+                if (dl < nsteps && (dl_use == 0 || poll(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
                     const uint32_t bar = bar_dofull0 + 8 * dl_st, dst = sdO0 + dl_st * C::TILE_BYTES;
                     mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
@@ -1116,6 +1121,291 @@ __device__ __forceinline__ void bwd_dq_body(const CUtensorMap* tmK, const CUtens
     if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
+// =====================================================================================================
+// dQ kernel v2 (round 2): same CTA decomposition as bwd_dq_body, but no tile ever waits for a buffer another tile still
+// occupies.  v1 kept S(j), dP(j) and dS(j) in ONE buffer (j&1), so dP(j) could only be issued once S(j) was in registers
+// and the compute warps then sat ~480 cycles per step waiting for it (trace: profiles/r1_bwd_v4_trace_dq.txt); here
+//   S  always lands in [128,256), dP in [256,384), dS (16-bit) in its own 64 columns [64,128)
+// -- the columns v1 spent on dO, which is now a shared-memory A operand (one TMA load per CTA; dP = dO V^T is an SS MMA).
+// So  S(j+1) is issued as soon as S(j) is in registers, dP(j+1) as soon as dP(j) is, dQ(j) as soon as dS(j) is stored:
+// all three are in flight or done before the compute warps need them, and the step is bound by the warps' own work.
+//   TMEM: Q [0,64) | dS [64,128) | S [128,256) | dP [256,384) | dQ [384,384+D)
+//   SMEM: K ring 4 (K_j lives from S(j) to dQ(j)) | V ring 2 | dO_i
+//   tensor order per step j:  S(j+1)  dP(j+1)  dQ(j)
+template <int D, bool BF16>
+__device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUtensorMap* tmV, const CUtensorMap* tmdO, const BwdParams& p) {
+    using C = aule_kp::BwdDq2Cfg<D>;
+    constexpr int NK = C::NK, NV = C::NV;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_q = sb + C::OFF_BAR;            // compute -> issuer: Q_i is in TMEM (16 arrivals)
+    const uint32_t bar_do = bar_q + 8;                 // dO_i landed
+    const uint32_t bar_kfull0 = bar_do + 8;            // K stage s landed (+8s)
+    const uint32_t bar_kfree0 = bar_kfull0 + 8 * NK;   // dQ(j) complete (commit): K stage j%NK free (+8s)
+    const uint32_t bar_vfull0 = bar_kfree0 + 8 * NK;   // V stage s landed (+8s)
+    const uint32_t bar_vfree0 = bar_vfull0 + 8 * NV;   // dP(j) complete (commit): V stage j%NV free (+8s)
+    const uint32_t bar_s = bar_vfree0 + 8 * NV;        // S(j) complete (commit)
+    const uint32_t bar_dp = bar_s + 8;                 // dP(j) complete (commit)
+    const uint32_t bar_dsfree = bar_dp + 8;            // dQ(j) complete (commit): the dS columns may be rewritten
+    const uint32_t bar_sfree = bar_dsfree + 8;         // compute -> issuer: S(j) in registers (16)
+    const uint32_t bar_dpfree = bar_sfree + 8;         // compute -> issuer: dP(j) in registers (16)
+    const uint32_t bar_ds = bar_dpfree + 8;            // compute -> issuer: dS(j) in TMEM (16)
+    const uint32_t bar_done = bar_ds + 8;              // every MMA complete (commit)
+    static_assert(8 * (2 + 2 * NK + 2 * NV + 7) <= C::BAR_BYTES, "barrier area too small");
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
+    const uint32_t sK0 = sb + C::OFF_K, sV0 = sb + C::OFF_V, sdO = sb + C::OFF_DO;
+
+    if (threadIdx.x == 0) {
+        if (sb & 1023u) { printf("[aule] dynamic smem not 1024-aligned\n"); __trap(); }
+        mbar_init(bar_q, 16); mbar_init(bar_do, 1);
+        for (int i = 0; i < NK; ++i) { mbar_init(bar_kfull0 + 8 * i, 1); mbar_init(bar_kfree0 + 8 * i, 1); }
+        for (int i = 0; i < NV; ++i) { mbar_init(bar_vfull0 + 8 * i, 1); mbar_init(bar_vfree0 + 8 * i, 1); }
+        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_dsfree, 1); mbar_init(bar_done, 1);
+        mbar_init(bar_sfree, 16); mbar_init(bar_dpfree, 16); mbar_init(bar_ds, 16);
+        fence_mbar_init();
+        tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
+    }
+    if (warp == 16) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t COL_Q = 0, COL_DS = 64, COL_S = 128, COL_DP = 256, COL_DQ = 384;
+
+    // ---- which query block (last = heaviest under causal first)
+    const uint32_t per = p.Hq * p.B;
+    const uint32_t nqb = (p.Sq + 127) / 128, nkb = (p.Sk + 127) / 128;
+    const uint32_t irev = blockIdx.x / per;
+    const uint32_t bh = blockIdx.x - irev * per;                     // b * Hq + hq
+    const uint32_t i = p.causal ? (nqb - 1 - irev) : irev;
+    const uint32_t b = bh / p.Hq, hq = bh - b * p.Hq;
+    const uint32_t bkv = b * p.Hkv + hq / (p.Hq / p.Hkv);
+    const uint32_t n = p.causal ? min(nkb, i + 1) : nkb;             // key blocks 0..n-1 (top-left causal)
+
+    if (warp >= 16) {
+        // ===================================================== three issuer warps, one per MMA stream (one elected thread each).
+        // The three streams only meet through the compute warps (S(j+1) needs "S(j) in registers", dP(j+1) "dP(j) in
+        // registers", dQ(j) "dS(j) stored"), so one thread issuing all of them in a fixed order made every stream wait for the
+        // slowest event (head-of-line blocking), and that thread shares its scheduler with four issue-bound compute warps
+        // (trace: ~400 cycles per wait).  Warps 16 / 17 / 18 sit on three different schedulers.
+        if (elect_one()) {
+            constexpr uint64_t HI_K = smem_desc_hi(16, 1024);
+            constexpr uint64_t HI_MN = smem_desc_hi(C::CHUNK_BYTES, 1024);
+            constexpr uint32_t HI_K_HI = uint32_t(HI_K >> 32), HI_K_LO = uint32_t(HI_K);
+            constexpr uint32_t HI_MN_HI = uint32_t(HI_MN >> 32), HI_MN_LO = uint32_t(HI_MN);
+            auto mk = [](uint32_t hi, uint32_t lo) -> uint64_t { return (uint64_t(hi) << 32) | lo; };
+            constexpr uint32_t ID_KK = instr_desc_f16(BF16, 128, 128, false);
+            constexpr uint32_t ID_KMN = instr_desc_f16(BF16, 128, D, true);
+            if (warp == 16) {
+                // ---- S stream + K loads: K(m) -> stage m%NK once dQ(m-NK) has released it
+                Tracer tr(p.trace, 0, true);
+                uint32_t kl = 0, kl_st = 0, kl_use = 0;                       // next K load, its stage, earlier fills of that stage
+                auto pump = [&]() {
+                    if (kl < n && (kl_use == 0 || mbar_test(bar_kfree0 + 8 * kl_st, (kl_use - 1) & 1))) {
+                        const uint32_t bar = bar_kfull0 + 8 * kl_st;
+                        mbar_expect_tx(bar, C::TILE_BYTES);
+#pragma unroll
+                        for (int c = 0; c < C::CHUNKS; ++c)
+                            tma_load_3d(sK0 + kl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmK, bar, c * 64, (int32_t)(kl * 128), (int32_t)bkv);
+                        ++kl;
+                        if (++kl_st == NK) { kl_st = 0; ++kl_use; }
+                    }
+                };
+                auto issue_s = [&](uint32_t j) {                             // S(j) = Q K_j^T (A = Q in TMEM)
+                    const uint32_t sK = sK0 + (j % NK) * C::TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
+                        mma_ts(tmem + COL_S, tmem + COL_Q + kk * 8, mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), ID_KK, kk > 0);
+                    }
+                    mma_commit(bar_s);
+                };
+                for (int t = 0; t < NK; ++t) pump();
+                mbar_wait(bar_q, 0);
+                mbar_wait(bar_kfull0, 0);
+                tc_fence_after();
+                issue_s(0);
+                for (uint32_t j = 0; j + 1 < n; ++j) {
+                    pump();
+                    tr.ev(10, j);
+                    mbar_wait(bar_sfree, j & 1);                             // S(j) is in registers
+                    tr.ev(16, j);
+                    while (!mbar_try_wait<0>(bar_kfull0 + 8 * ((j + 1) % NK), ((j + 1) / NK) & 1)) pump();
+                    tc_fence_after();
+                    issue_s(j + 1);
+                    tr.ev(18, j);
+                }
+                while (kl < n) pump();                                       // (every load is requested before its consumer waits; nothing left here)
+            } else if (warp == 17) {
+                // ---- dP stream + dO / V loads: V(m) -> stage m%NV once dP(m-NV) has released it
+                uint32_t vl = 0, vl_st = 0, vl_use = 0;
+                auto pump = [&]() {
+                    if (vl < n && (vl_use == 0 || mbar_test(bar_vfree0 + 8 * vl_st, (vl_use - 1) & 1))) {
+                        const uint32_t bar = bar_vfull0 + 8 * vl_st;
+                        mbar_expect_tx(bar, C::TILE_BYTES);
+#pragma unroll
+                        for (int c = 0; c < C::CHUNKS; ++c)
+                            tma_load_3d(sV0 + vl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmV, bar, c * 64, (int32_t)(vl * 128), (int32_t)bkv);
+                        ++vl;
+                        if (++vl_st == NV) { vl_st = 0; ++vl_use; }
+                    }
+                };
+                auto issue_dp = [&](uint32_t j) {                            // dP(j) = dO V_j^T (A = dO in shared memory)
+                    const uint32_t sV = sV0 + (j % NV) * C::TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
+                        mma_ss(tmem + COL_DP, mk(HI_K_HI, (HI_K_LO | (sdO >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sV >> 4)) + off), ID_KK, kk > 0);
+                    }
+                    mma_commit(bar_dp);
+                    mma_commit(bar_vfree0 + 8 * (j % NV));
+                };
+                mbar_expect_tx(bar_do, C::TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < C::CHUNKS; ++c) tma_load_3d(sdO + c * C::CHUNK_BYTES, tmdO, bar_do, c * 64, (int32_t)(i * 128), (int32_t)bh);
+                for (int t = 0; t < NV; ++t) pump();
+                mbar_wait(bar_do, 0);
+                mbar_wait(bar_vfull0, 0);
+                tc_fence_after();
+                issue_dp(0);
+                for (uint32_t j = 0; j + 1 < n; ++j) {
+                    pump();
+                    mbar_wait(bar_dpfree, j & 1);                            // dP(j) is in registers
+                    while (!mbar_try_wait<0>(bar_vfull0 + 8 * ((j + 1) % NV), ((j + 1) / NV) & 1)) pump();
+                    tc_fence_after();
+                    issue_dp(j + 1);
+                }
+            } else if (warp == 18) {
+                // ---- dQ stream
+                for (uint32_t j = 0; j < n; ++j) {
+                    const uint32_t sK = sK0 + (j % NK) * C::TILE_BYTES;
+                    mbar_wait(bar_ds, j & 1);                                // dS(j) in TMEM
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)                           // dQ += dS(j) K_j (K = 128 keys, A = dS in TMEM)
+                        mma_ts(tmem + COL_DQ, tmem + COL_DS + 8 * kk, mk(HI_MN_HI, (HI_MN_LO | (sK >> 4)) + kk * 128), ID_KMN, (j > 0 || kk > 0) ? 1u : 0u);
+                    mma_commit(bar_kfree0 + 8 * (j % NK));
+                    mma_commit(bar_dsfree);
+                }
+                mma_commit(bar_done);                                        // dQ(n-1) is the last MMA: its dS needed every S and dP
+            }
+        }
+    } else {
+        // ===================================================== compute warps
+        const uint32_t qt = warp >> 2;                               // key quarter: columns [32qt, 32qt+32)
+        const uint32_t h = (warp >> 2) & 1;                          // epilogue (warps 0-7): D half
+        const uint32_t r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = ((warp & 3) * 32) << 16;
+        const uint32_t row = i * 128 + r;
+        const size_t stat_off = (size_t)bh * p.Sq;
+        const bool row_ok = row < p.Sq;
+        // ---- Q_i: this thread's D/4 elements of its row -> TMEM (A operand of S = Q K^T), zero beyond Sq
+        {
+            constexpr int NR = D / 8;                                // 32-bit registers per thread
+            uint32_t a[NR];
+            // (padded head dims: rows are D_real elements apart in memory, columns >= D_real are zero -- D_real % 8 == 0, so a
+            //  16-byte vector is either entirely real or entirely padding)
+            const size_t eoff = ((stat_off + (row_ok ? row : 0)) * p.D_real + (D / 4) * qt) * 2;
+            const uint4* gq = reinterpret_cast<const uint4*>(static_cast<const char*>(p.q) + eoff);
+#pragma unroll
+            for (int u = 0; u < NR / 4; ++u) {
+                const uint4 x = (row_ok && (D / 4) * qt + 8 * u < p.D_real) ? gq[u] : make_uint4(0, 0, 0, 0);
+                a[4 * u] = x.x; a[4 * u + 1] = x.y; a[4 * u + 2] = x.z; a[4 * u + 3] = x.w;
+            }
+            if constexpr (NR == 16) tmem_st16(tmem + lane_addr + COL_Q + NR * qt, a);
+            else tmem_st8(tmem + lane_addr + COL_Q + NR * qt, a);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_q);
+        }
+        const float lse2 = row_ok ? p.lse[stat_off + row] * 1.4426950408889634f : 0.f;
+        const float delta = row_ok ? p.delta[stat_off + row] : 0.f;
+        const uint32_t tS = tmem + lane_addr + COL_S + 32 * qt, tDP = tmem + lane_addr + COL_DP + 32 * qt;
+        const uint32_t tDS = tmem + lane_addr + COL_DS + 16 * qt;
+        Tracer tr(p.trace, 1 + (qt & 1), (warp == 0 || warp == 4) && lane == 0);
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t key0 = j * 128;
+            const bool diag = p.causal && (i * 128 < key0 + 128);
+            const bool masked = diag || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
+            // ---- P phase
+            float pv[32];
+            tr.ev(20, j);
+            mbar_wait(bar_s, j & 1);
+            tr.ev(21, j);
+            tc_fence_after();
+            {
+                uint32_t s[32];
+                tmem_ld32(tS, s);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sfree);               // the S columns may take S(j+1)
+                tr.ev(22, j);
+                if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
+                else p_from_s<false, 1>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
+            }
+            // ---- dS phase: dS = P o (dP - Delta) -> 16-bit -> this quarter's 16 of the 64 dS columns
+            tr.ev(23, j);
+            mbar_wait(bar_dp, j & 1);
+            tr.ev(24, j);
+            tc_fence_after();
+            uint32_t pk[16];
+            {
+                uint32_t dp[32];
+                tmem_ld32(tDP, dp);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dpfree);              // the dP columns may take dP(j+1)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float2 a = __fmul2_rn(make_float2(pv[2 * e], pv[2 * e + 1]),
+                                                __fadd2_rn(make_float2(__uint_as_float(dp[2 * e]), __uint_as_float(dp[2 * e + 1])), make_float2(-delta, -delta)));
+                    pk[e] = pack2<BF16>(a.x, a.y);
+                }
+            }
+            tr.ev(25, j);
+            if (j > 0) mbar_wait(bar_dsfree, (j - 1) & 1);           // dQ(j-1) has read dS(j-1)
+            tc_fence_after();
+            tmem_st16(tDS, pk);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ds);
+            tr.ev(27, j);
+        }
+        // ---- epilogue: dQ (x scale) -> 16-bit -> global (this half's D/2 columns of the row: 64 or 128 contiguous bytes)
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        if (warp < 8) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.dq_out) + ((stat_off + (row_ok ? row : 0)) * p.D_real + (D / 2) * h) * 2);
+#pragma unroll 1
+            for (int c = 0; c < D / 64; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tmem + lane_addr + COL_DQ + (D / 2) * h + c * 32, o);
+                tmem_wait_ld();
+                if (row_ok) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if ((D / 2) * h + c * 32 + 8 * u >= p.D_real) break;       // padding columns
+                        uint4 v;
+                        v.x = pack2<BF16>(__uint_as_float(o[8 * u + 0]) * p.scale, __uint_as_float(o[8 * u + 1]) * p.scale);
+                        v.y = pack2<BF16>(__uint_as_float(o[8 * u + 2]) * p.scale, __uint_as_float(o[8 * u + 3]) * p.scale);
+                        v.z = pack2<BF16>(__uint_as_float(o[8 * u + 4]) * p.scale, __uint_as_float(o[8 * u + 5]) * p.scale);
+                        v.w = pack2<BF16>(__uint_as_float(o[8 * u + 6]) * p.scale, __uint_as_float(o[8 * u + 7]) * p.scale);
+                        dst[c * 4 + u] = v;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace bwd100
 
 #define AULE_BWD100(NAME, DD, BF)                                                                        \
@@ -1157,10 +1447,25 @@ AULE_BWD100(aule_bwd_sm100_bf16_d64, 64, true)
 AULE_BWD100(aule_bwd_sm100_f16_d128, 128, false)
 AULE_BWD100(aule_bwd_sm100_f16_d64, 64, false)
 #endif
-AULE_BWD100_DQ(aule_bwd_dq_sm100_bf16_d128, 128, true)
-AULE_BWD100_DQ(aule_bwd_dq_sm100_bf16_d64, 64, true)
-AULE_BWD100_DQ(aule_bwd_dq_sm100_f16_d128, 128, false)
-AULE_BWD100_DQ(aule_bwd_dq_sm100_f16_d64, 64, false)
+#define AULE_BWD100_DQ2(NAME, DD, BF)                                                                    \
+    extern "C" __global__ void __launch_bounds__(608, 1) NAME(const __grid_constant__ CUtensorMap tmK,    \
+                                                              const __grid_constant__ CUtensorMap tmV,    \
+                                                              const __grid_constant__ CUtensorMap tmdO,   \
+                                                              const aule_kp::BwdParams p) {               \
+        bwd100::bwd_dq2_body<DD, BF>(&tmK, &tmV, &tmdO, p);                                               \
+    }
+AULE_BWD100_DQ2(aule_bwd_dq_sm100_bf16_d128, 128, true)
+AULE_BWD100_DQ2(aule_bwd_dq_sm100_bf16_d64, 64, true)
+AULE_BWD100_DQ2(aule_bwd_dq_sm100_f16_d128, 128, false)
+AULE_BWD100_DQ2(aule_bwd_dq_sm100_f16_d64, 64, false)
+#ifdef AULE_TUNING_VARIANTS
+// the superseded v1 dQ kernel (S, dP and dS of a step share one TMEM buffer; Q and dO both in TMEM): tuning builds only
+// (aule_set_kernel_path bit 23)
+AULE_BWD100_DQ(aule_bwd_dq1_sm100_bf16_d128, 128, true)
+AULE_BWD100_DQ(aule_bwd_dq1_sm100_bf16_d64, 64, true)
+AULE_BWD100_DQ(aule_bwd_dq1_sm100_f16_d128, 128, false)
+AULE_BWD100_DQ(aule_bwd_dq1_sm100_f16_d64, 64, false)
+#endif
 
 // Delta_i = sum_d O_id dO_id (triton_flash.py:353-379), one warp per row.
 template <typename T>

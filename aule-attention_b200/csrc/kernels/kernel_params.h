@@ -120,6 +120,7 @@ struct BwdParams {
     int32_t causal;
     int32_t order;            // reserved for A/B tuning of the MMA issue order (unused by the shipped kernels)
     unsigned long long* trace; // bring-up: CTA 0 records (tag << 48 | clock64) events here (3 x 4096 entries) or nullptr
+    uint32_t D_real;          // head_dim of the tensors in memory (<= the kernel's D: TMA zero-fills / clips the padding columns)
     float* dq_acc;            // fused kernel: [B,Hq,Sq,D] fp32 dQ accumulator (zeroed by the host, converted by aule_bwd_dq_convert_*)
 };
 template <int D>
@@ -200,6 +201,25 @@ struct BwdDqCfg {
     static constexpr uint32_t BAR_BYTES = 192;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+};
+
+// dQ kernel v2: K ring (4) | V ring (2) | dO_i tile | barriers   (Q and dS live in TMEM, dO is a shared-memory A operand)
+template <int D>
+struct BwdDq2Cfg {
+    static_assert(D == 64 || D == 128, "head_dim must be 64 or 128 on the tensor-core path");
+    static constexpr int THREADS = 608;                         // 16 compute warps + 3 issuer warps (S, dP, dQ streams)
+    static constexpr int NK = 4, NV = 2;
+    static constexpr int CHUNKS = D / 64;
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_K = 0;
+    static constexpr uint32_t OFF_V = NK * TILE_BYTES;
+    static constexpr uint32_t OFF_DO = (NK + NV) * TILE_BYTES;
+    static constexpr uint32_t OFF_BAR = (NK + NV + 1) * TILE_BYTES;
+    static constexpr uint32_t BAR_BYTES = 192;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
 

@@ -65,6 +65,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Wait until the phase with the given parity has completed.
+// Non-blocking poll (mbarrier.test_wait never suspends the thread): for "is this stage free yet?" checks made on the side of
+// another wait -- a try_wait on a barrier that is not complete may sleep for the hardware's time limit.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 template <uint32_t HINT_NS = 1000000u>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if AULE_WATCHDOG

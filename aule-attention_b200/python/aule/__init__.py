@@ -196,9 +196,6 @@ def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.
                       or key.dtype != query.dtype or value.dtype != query.dtype
                       or (is_causal and query.shape[-2] != key.shape[-2])      # SDPA's causal is top-left too, but be strict
                       or (query.shape[1] != key.shape[1] and not enable_gqa))
-    if not needs_fallback and query.shape[-1] not in (64, 128):
-        # padded head dims have a tensor-core forward only; their backward runs the CUDA-core kernels: keep training on SDPA
-        needs_fallback = torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad)
     if needs_fallback:
         fn = _original_sdpa if _original_sdpa is not None else torch.nn.functional.scaled_dot_product_attention
         if fn is scaled_dot_product_attention:

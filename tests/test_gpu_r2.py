@@ -135,6 +135,31 @@ def test_sliding_window_backward(aule, dtype, causal, window):
         assert orc.rel_err_to_scale(g_.float().cpu().numpy(), e_) <= tol
 
 
+# ------------------------------------------------------------------ padded head dims: tensor-core backward
+@pytest.mark.parametrize("D", [8, 40, 56, 80, 96, 120])
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,causal", [(1, 4, 2, 200, 200, True), (2, 2, 2, 384, 384, True), (1, 2, 1, 100, 333, False)])
+def test_padded_head_dim_backward_on_tensor_cores(aule, D, dtype, B, Hq, Hkv, Sq, Sk, causal):
+    """Training with head dims the reference pads to a power of two (triton_flash.py:446): the tensor-core backward runs at
+    64 / 128 with the padding columns zero-filled by TMA (Q, K, V, dO), clipped on store (dK, dV) and predicated in the dQ
+    kernel's own loads / stores.  Expected values: the oracle's analytic gradients."""
+    import torch
+    from aule import ffi
+    td = {"bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    q, k, v = ref_inputs(B, Hq, Sq, D, Hkv=Hkv, Sk=Sk)
+    tq, tk, tv = (torch.from_numpy(np.ascontiguousarray(x)).cuda().to(td).requires_grad_() for x in (q, k, v))
+    out = aule.flash_attention(tq, tk, tv, causal=causal)
+    do = torch.randn(out.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(D)).to(td)
+    out.backward(do)
+    torch.cuda.synchronize()
+    assert ffi.load_library().aule_last_kernel().decode() == f"aule_bwd_dq_sm100_{dtype}_d{64 if D <= 64 else 128}"
+    edq, edk, edv, _, _ = orc.attention_bwd_ref(*(t.detach().float().cpu().numpy() for t in (tq, tk, tv, do)), causal=causal)
+    for g_, e_ in ((tq.grad, edq), (tk.grad, edk), (tv.grad, edv)):
+        g = g_.float().cpu().numpy()
+        assert np.isfinite(g).all()
+        assert orc.rel_err_to_scale(g, e_) <= BF16_TOL, orc.rel_err_to_scale(g, e_)
+
+
 # ------------------------------------------------------------------ fused backward (opt-in)
 @pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,causal,dtype", [
     (1, 2, 1, 256, 256, True, "bf16"), (2, 4, 2, 1000, 1000, True, "f16"), (1, 2, 1, 300, 520, False, "bf16"), (1, 8, 2, 1536, 1536, True, "bf16")])
@@ -416,6 +441,9 @@ def test_sdpa_shim_only_routes_tensor_core_shapes(aule):
     assert lib.aule_launch_count() == n0 + 1 and lib.aule_last_kernel().decode() == "aule_fwd_sm100_bf16_d64"
     ref = F.scaled_dot_product_attention(q.float(), q.float(), q.float(), is_causal=True)
     assert (o.float() - ref).abs().max().item() <= 2e-2
+    qg = q.clone().requires_grad_()                                        # padded-D training is routed too (tensor-core backward)
+    aule.scaled_dot_product_attention(qg, qg, qg, is_causal=True).sum().backward()
+    assert lib.aule_last_kernel().decode() == "aule_bwd_dq_sm100_bf16_d64" and torch.isfinite(qg.grad).all()
     n0 = lib.aule_launch_count()
     aule.scaled_dot_product_attention(q.float(), q.float(), q.float(), is_causal=True)     # fp32 -> original SDPA
     q2 = torch.randn(1, 4, 128, 36, device="cuda", dtype=torch.bfloat16)

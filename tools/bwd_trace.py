@@ -65,6 +65,9 @@ if which == "fused":
              15: "iss: P half1 ok -> dV odd", 16: "iss: Q(s+2) ok -> S(s+2)",
              20: "cmp: wait dP", 21: "cmp: dP ok", 22: "cmp: dS math done", 23: "cmp: dS stored+fenced", 24: "cmp: S(s+1) ok",
              25: "cmp: P half0 published", 26: "cmp: dQ^T ok", 27: "cmp: drained"}
+if which == "dq":
+    names.update({10: "iss: step top (dQ(j-1) issued)", 16: "iss: sfree ok", 11: "iss: K(j+1) ok -> S(j+1)", 18: "iss: S(j+1) issued", 17: "iss: dpfree ok",
+                  12: "iss: V(j+1) ok -> dP(j+1)", 19: "iss: dP(j+1) issued", 13: "iss: dS(j) ok -> dQ(j)"})
 for t, region, code, step in rows:
     if lo <= step <= hi:
         print(f"{t - t0:9d}  r{region} step {step:3d}  {code:3d} {names.get(code, '')}")
