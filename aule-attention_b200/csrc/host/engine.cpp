@@ -423,11 +423,12 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     // zero-fill the padding columns of Q, K, V, dO and clip them from dK, dV; the dQ kernel predicates its own loads and
     // stores), causal / full masks.  A sliding window (the reference's backward ignores it, triton_flash.py:313-319 -- its
     // gradients are then wrong), fp32 and head dims that are not a multiple of 8 run the deterministic CUDA-core kernels.
-    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D % 8 == 0) && path_ != kForceCudaCore && window < 0 &&
-                    ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0 && !(bwd_dq_v1_ && s.D != 64 && s.D != 128);
+    const bool legacy_kernels = bwd_dq_v1_ || (bwd_serial_ & 2);       // tuning builds: v1 dQ / v3 dK/dV kernels know neither
+    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D % 8 == 0) && path_ != kForceCudaCore &&
+                    ((q | k | v | o | d_o | dq | dk | dv) & 15) == 0 && !(legacy_kernels && ((s.D != 64 && s.D != 128) || window > 0));
     if (!tc && log_enabled())
         fprintf(stderr, "[aule] backward [%u,%u(%u),%u/%u,%u] %s: CUDA-core kernels (%s)\n", s.B, s.Hq, s.Hkv, s.Sq, s.Sk, s.D,
-                kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : window > 0 ? "sliding window" : "head_dim % 8 != 0 or unaligned pointers");
+                kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : "head_dim % 8 != 0 or unaligned pointers");
     if (tc) {
         // Tensor-core backward: Delta pre-pass, then the dK/dV kernel (key block outer) and the dQ kernel (query block
         // outer).  No atomics and no workspace beyond Delta: bit-reproducible.
@@ -454,6 +455,9 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             BwdParams bp;
             bp.dq_out = (void*)dq; bp.q = (const void*)q; bp.d_o = (const void*)d_o; bp.lse = (const float*)lse; bp.delta = (const float*)delta;
             bp.B = s.B; bp.Hq = s.Hq; bp.Hkv = s.Hkv; bp.Sq = s.Sq; bp.Sk = s.Sk; bp.D_real = s.D;
+            // same band as the forward (attention_f32.comp:173-183): causal window keeps 0 <= i-j < W, bidirectional |i-j| <= W/2
+            bp.win_right = causal ? 0u : (window > 0 ? (uint32_t)window / 2 : aule_kp::kWinInf);
+            bp.win_left = window > 0 ? (causal ? (uint32_t)window - 1 : (uint32_t)window / 2) : aule_kp::kWinInf;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
             bp.order = bwd_serial_ | (bwd_legacy_poll_ ? 4 : 0);
             // dK/dV CTA order: all units at once.  Launching the KV-block CTAs of a few (batch, kv-head) units together
@@ -465,7 +469,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
-            if (e.empty() && bwd_fused_ && s.D == 128 && bwd_order_ == 0) {
+            if (e.empty() && bwd_fused_ && s.D == 128 && bwd_order_ == 0 && window < 0) {
                 // Fused backward (attn_bwd_fused_sm100.cu): dK / dV as below, dQ reduced into an fp32 accumulator that is
                 // zeroed here and converted (x scale) afterwards.
                 const size_t n = (size_t)s.B * s.Hq * s.Sq * s.D;

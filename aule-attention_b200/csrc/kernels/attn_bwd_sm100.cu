@@ -105,6 +105,25 @@ __device__ __forceinline__ void p_from_s(const uint32_t (&s)[32], float* pv, flo
     }
 }
 
+// Same for a block on the edge of the visibility band row - win_left <= key <= row + win_right (causal: win_right = 0) or on
+// a ragged end: visible local columns [max(row - win_left, 0), min(row + win_right, Sk - 1)] - col0.
+__device__ __forceinline__ void p_from_s_band(const uint32_t (&s)[32], float* pv, float c2, float lse2, uint32_t col0, uint32_t row,
+                                              uint32_t Sk, bool row_ok, uint32_t win_left, uint32_t win_right) {
+    const int64_t first = (int64_t)row - (int64_t)win_left - (int64_t)col0;
+    const int64_t last = min((int64_t)Sk - 1, (int64_t)row + (int64_t)win_right) - (int64_t)col0;
+    const uint32_t lo_m = first <= 0 ? 0xffffffffu : (first > 31 ? 0u : (0xffffffffu << (int)first));
+    const uint32_t hi_m = last >= 31 ? 0xffffffffu : (last < 0 ? 0u : (0xffffffffu >> (31 - (int)last)));
+    const uint32_t alive = row_ok ? (lo_m & hi_m) : 0u;
+    const float2 cc = make_float2(c2, c2), nl = make_float2(-lse2, -lse2);
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), cc, nl);
+        const float vx = ex2(x.x), vy = ex2(x.y);
+        pv[e] = (alive & (1u << e)) ? vx : 0.f;          // select, not multiply: a row without any visible key has LSE = -inf
+        pv[e + 1] = (alive & (2u << e)) ? vy : 0.f;
+    }
+}
+
 // 32 values of one row -> 16-bit -> swizzled [128 rows][64 elements] sub-tile (4 x 16-byte units, unit index (c*4+u) ^ (r&7))
 template <bool BF16>
 __device__ __forceinline__ void store_row32(uint32_t base, uint32_t r, int c, const float* v) {
@@ -517,8 +536,10 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
     const uint32_t group = p.Hq / p.Hkv;
     const uint32_t key0 = jb * 128;
     const uint32_t nqb = (p.Sq + 127) / 128;
-    const uint32_t i_begin = p.causal ? jb : 0;                      // query blocks with rows >= key0 (top-left causal)
-    const uint32_t steps_per_head = (i_begin < nqb) ? (nqb - i_begin) : 0;
+    // query blocks whose rows can see a key of this block: key - win_right <= q <= key + win_left (causal: win_right = 0)
+    const uint32_t i_begin = key0 > p.win_right ? (key0 - p.win_right) / 128 : 0;
+    const uint32_t i_end = (uint32_t)min((uint64_t)nqb, ((uint64_t)key0 + 127 + p.win_left) / 128 + 1);
+    const uint32_t steps_per_head = (i_begin < i_end) ? (i_end - i_begin) : 0;
     const uint32_t nsteps = steps_per_head * group;
 
     if (warp == 16) {
@@ -547,7 +568,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     for (int c = 0; c < C::CHUNKS; ++c)
                         tma_load_3d(dst + c * C::CHUNK_BYTES, tmQ, bar, c * 64, (int32_t)(ql_i * 128), (int32_t)(b * p.Hq + hk * group + ql_g));
                     ++ql;
-                    if (++ql_i == nqb) { ql_i = i_begin; ++ql_g; }
+                    if (++ql_i == i_end) { ql_i = i_begin; ++ql_g; }
                     if (++ql_st == NQ) { ql_st = 0; ++ql_use; }
                 }
                 if (dl < nsteps && (dl_use == 0 || poll(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
@@ -557,7 +578,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     for (int c = 0; c < C::CHUNKS; ++c)
                         tma_load_3d(dst + c * C::CHUNK_BYTES, tmdO, bar, c * 64, (int32_t)(dl_i * 128), (int32_t)(b * p.Hq + hk * group + dl_g));
                     ++dl;
-                    if (++dl_i == nqb) { dl_i = i_begin; ++dl_g; }
+                    if (++dl_i == i_end) { dl_i = i_begin; ++dl_g; }
                     if (++dl_st == NDO) { dl_st = 0; ++dl_use; }
                 }
             };
@@ -671,7 +692,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             const bool ok = row < p.Sq;
             lse_n = ok ? p.lse[off + row] : 0.f;
             delta_n = ok ? p.delta[off + row] : 0.f;
-            if (++i_n == nqb) { i_n = i_begin; ++g_n; }
+            if (++i_n == i_end) { i_n = i_begin; ++g_n; }
         };
         auto publish = [&](uint32_t s_) {                            // statistics of step s_ -> buffer s_&1, one arrival per warp
             float* sn = stat + (s_ & 1) * 256;
@@ -690,13 +711,16 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             mbar_wait(bar_stat0 + 8 * (step & 1), (step >> 1) & 1);  // statistics of this step are visible
             const float* sc = stat + (step & 1) * 256 + 32 * qt;     // this quarter's 32 lse2, then (+128) its 32 deltas
             const uint32_t q0 = i * 128 + 32 * qt;                   // first query of this thread's columns
-            const bool diag = p.causal && (i * 128 < key0 + 128);
-            const bool masked = diag || !key_ok || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
-            if (++i == nqb) i = i_begin;
+            // the block is inside the band when its last key sees its first query (key0+127 - win_right <= i*128) and its
+            // first key sees its last query (i*128+127 <= key0 + win_left)
+            const bool edge = (uint64_t)key0 + 127 > (uint64_t)i * 128 + p.win_right || (uint64_t)i * 128 + 127 > (uint64_t)key0 + p.win_left;
+            const bool masked = edge || !key_ok || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
+            if (++i == i_end) i = i_begin;
 
             uint32_t alive = 0xffffffffu;
-            if (masked) {
-                const int64_t first = diag ? (int64_t)key - (int64_t)q0 : 0, last = (int64_t)p.Sq - 1 - (int64_t)q0;
+            if (masked) {                                            // visible queries of this key: [key - win_right, min(key + win_left, Sq - 1)]
+                const int64_t first = (int64_t)key - (int64_t)p.win_right - (int64_t)q0;
+                const int64_t last = min((int64_t)p.Sq - 1, (int64_t)key + (int64_t)p.win_left) - (int64_t)q0;
                 const uint32_t lo_m = first <= 0 ? 0xffffffffu : (first > 31 ? 0u : (0xffffffffu << (int)first));
                 const uint32_t hi_m = last >= 31 ? 0xffffffffu : (last < 0 ? 0u : (0xffffffffu >> (31 - (int)last)));
                 alive = key_ok ? (lo_m & hi_m) : 0u;
@@ -1181,7 +1205,11 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
     const uint32_t i = p.causal ? (nqb - 1 - irev) : irev;
     const uint32_t b = bh / p.Hq, hq = bh - b * p.Hq;
     const uint32_t bkv = b * p.Hkv + hq / (p.Hq / p.Hkv);
-    const uint32_t n = p.causal ? min(nkb, i + 1) : nkb;             // key blocks 0..n-1 (top-left causal)
+    // key blocks a row of this query block can see: row - win_left <= key <= row + win_right (causal: win_right = 0);
+    // the kernel numbers them j = 0..n-1 from j0
+    const uint32_t j0 = i * 128 > p.win_left ? (i * 128 - p.win_left) / 128 : 0;
+    const uint32_t j_end = (uint32_t)min((uint64_t)nkb, ((uint64_t)i * 128 + 127 + p.win_right) / 128 + 1);
+    const uint32_t n = j_end > j0 ? j_end - j0 : 0;
 
     if (warp >= 16) {
         // ===================================================== three issuer warps, one per MMA stream (one elected thread each).
@@ -1189,7 +1217,7 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
         // registers", dQ(j) "dS(j) stored"), so one thread issuing all of them in a fixed order made every stream wait for the
         // slowest event (head-of-line blocking), and that thread shares its scheduler with four issue-bound compute warps
         // (trace: ~400 cycles per wait).  Warps 16 / 17 / 18 sit on three different schedulers.
-        if (elect_one()) {
+        if (elect_one() && n > 0) {                                   // (n == 0: a query block beyond every key's window -- dQ = 0)
             constexpr uint64_t HI_K = smem_desc_hi(16, 1024);
             constexpr uint64_t HI_MN = smem_desc_hi(C::CHUNK_BYTES, 1024);
             constexpr uint32_t HI_K_HI = uint32_t(HI_K >> 32), HI_K_LO = uint32_t(HI_K);
@@ -1207,7 +1235,7 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
                         mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
                         for (int c = 0; c < C::CHUNKS; ++c)
-                            tma_load_3d(sK0 + kl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmK, bar, c * 64, (int32_t)(kl * 128), (int32_t)bkv);
+                            tma_load_3d(sK0 + kl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmK, bar, c * 64, (int32_t)((j0 + kl) * 128), (int32_t)bkv);
                         ++kl;
                         if (++kl_st == NK) { kl_st = 0; ++kl_use; }
                     }
@@ -1246,7 +1274,7 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
                         mbar_expect_tx(bar, C::TILE_BYTES);
 #pragma unroll
                         for (int c = 0; c < C::CHUNKS; ++c)
-                            tma_load_3d(sV0 + vl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmV, bar, c * 64, (int32_t)(vl * 128), (int32_t)bkv);
+                            tma_load_3d(sV0 + vl_st * C::TILE_BYTES + c * C::CHUNK_BYTES, tmV, bar, c * 64, (int32_t)((j0 + vl) * 128), (int32_t)bkv);
                         ++vl;
                         if (++vl_st == NV) { vl_st = 0; ++vl_use; }
                     }
@@ -1326,9 +1354,9 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
         const uint32_t tDS = tmem + lane_addr + COL_DS + 16 * qt;
         Tracer tr(p.trace, 1 + (qt & 1), (warp == 0 || warp == 4) && lane == 0);
         for (uint32_t j = 0; j < n; ++j) {
-            const uint32_t key0 = j * 128;
-            const bool diag = p.causal && (i * 128 < key0 + 128);
-            const bool masked = diag || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
+            const uint32_t key0 = (j0 + j) * 128;
+            const bool edge = (uint64_t)key0 + 127 > (uint64_t)i * 128 + p.win_right || (uint64_t)i * 128 + 127 > (uint64_t)key0 + p.win_left;
+            const bool masked = edge || key0 + 128 > p.Sk || i * 128 + 128 > p.Sq;
             // ---- P phase
             float pv[32];
             tr.ev(20, j);
@@ -1343,7 +1371,7 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sfree);               // the S columns may take S(j+1)
                 tr.ev(22, j);
-                if (masked) p_from_s<true>(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, diag);
+                if (masked) p_from_s_band(s, pv, p.scale_log2, lse2, key0 + 32 * qt, row, p.Sk, row_ok, p.win_left, p.win_right);
                 else p_from_s<false, 1>(s, pv, p.scale_log2, lse2, 0, 0, 0, true, false);
             }
             // ---- dS phase: dS = P o (dP - Delta) -> 16-bit -> this quarter's 16 of the 64 dS columns
@@ -1377,15 +1405,20 @@ __device__ __forceinline__ void bwd_dq2_body(const CUtensorMap* tmK, const CUten
             tr.ev(27, j);
         }
         // ---- epilogue: dQ (x scale) -> 16-bit -> global (this half's D/2 columns of the row: 64 or 128 contiguous bytes)
-        mbar_wait(bar_done, 0);
+        if (n > 0) mbar_wait(bar_done, 0);
         tc_fence_after();
         if (warp < 8) {
             uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.dq_out) + ((stat_off + (row_ok ? row : 0)) * p.D_real + (D / 2) * h) * 2);
 #pragma unroll 1
             for (int c = 0; c < D / 64; ++c) {
                 uint32_t o[32];
-                tmem_ld32(tmem + lane_addr + COL_DQ + (D / 2) * h + c * 32, o);
-                tmem_wait_ld();
+                if (n > 0) {
+                    tmem_ld32(tmem + lane_addr + COL_DQ + (D / 2) * h + c * 32, o);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = 0u;
+                }
                 if (row_ok) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {

@@ -120,6 +120,7 @@ struct BwdParams {
     int32_t causal;
     int32_t order;            // reserved for A/B tuning of the MMA issue order (unused by the shipped kernels)
     unsigned long long* trace; // bring-up: CTA 0 records (tag << 48 | clock64) events here (3 x 4096 entries) or nullptr
+    uint32_t win_left, win_right;   // visibility band i - win_left <= j <= i + win_right (kWinInf = unbounded; causal: win_right = 0)
     uint32_t D_real;          // head_dim of the tensors in memory (<= the kernel's D: TMA zero-fills / clips the padding columns)
     float* dq_acc;            // fused kernel: [B,Hq,Sq,D] fp32 dQ accumulator (zeroed by the host, converted by aule_bwd_dq_convert_*)
 };
