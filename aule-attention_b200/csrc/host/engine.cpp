@@ -149,6 +149,10 @@ std::string Engine::load_device(int ordinal) {
                                     dd ? (int)aule_kp::BwdDqCfg<128>::SMEM_BYTES : (int)aule_kp::BwdDqCfg<64>::SMEM_BYTES);
         }
     }
+    if (e.empty()) e = get(&d.fwd_tf32, "aule_fwd_sm100_tf32_d64");
+    if (e.empty())
+        e = check(drv_.cuFuncSetAttribute(d.fwd_tf32, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                          (int)aule_kp::FwdCfgT32::SMEM_BYTES), "cuFuncSetAttribute(smem fwd tf32)");
     for (int t = 1; t < 3 && e.empty(); ++t) {
         e = get(&d.bwd_fused_sm100[t], std::string("aule_bwd_fused_sm100_") + kDtypeSuffix[t] + "_d128");
         if (e.empty()) e = get(&d.bwd_dq_convert[t], std::string("aule_bwd_dq_convert_") + kDtypeSuffix[t]);
@@ -253,7 +257,7 @@ Device* Engine::by_ordinal(int ordinal) {
 
 std::string Engine::validate(const AttnShape& s, int32_t dtype) {
     char buf[256];
-    if (dtype < 0 || dtype > 2) return "unsupported dtype (0=f32, 1=bf16, 2=f16)";
+    if (dtype < 0 || dtype > 3) return "unsupported dtype (0=f32, 1=bf16, 2=f16, 3=f32 tensors with tf32 tensor-core math allowed)";
     if (!s.B || !s.Hq || !s.Hkv || !s.Sq || !s.Sk || !s.D) return "empty tensor dimension";
     if (s.Hq % s.Hkv != 0) {   // attention_gpu.zig:383-388, __init__.py:159-160
         snprintf(buf, sizeof(buf), "heads_q (%u) must be divisible by heads_kv (%u) for GQA", s.Hq, s.Hkv);
@@ -278,18 +282,23 @@ std::string Engine::launch(Device& d, CUfunction fn, const char* name, unsigned 
     return e;
 }
 
-std::string Engine::make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D) const {
-    // [bh, S, D] 16-bit row-major viewed as a 3-D tensor (D innermost); box = 64 x 128 x 1 with the
-    // 128-byte swizzle the UMMA descriptors in attn_fwd_sm100.cu expect. Out-of-range rows read as 0
-    // and are clipped on store, which is how ragged Sq/Sk tails are handled.
+std::string Engine::make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D,
+                              bool mn_major_f32) const {
+    // [bh, S, D] row-major viewed as a 3-D tensor (D innermost); box = 128 bytes x 128 rows x 1 (64 16-bit or 32 fp32
+    // elements) with the 128-byte swizzle the UMMA descriptors in attn_fwd_sm100.cu expect. Out-of-range rows / columns
+    // read as 0 and are clipped on store, which is how ragged Sq/Sk tails and padded head dims are handled.
+    // mn_major_f32: the V operand of the tf32 kernel -- 32-bit MN-major operands need the 128-byte swizzle with 32-byte atoms.
+    const bool f32 = dtype == kF32 || dtype == kTF32;
+    const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[3] = {D, S, bh};
-    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)S * D * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)D * es, (cuuint64_t)S * D * es};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = drv_.cuTensorMapEncodeTiled(
-        m, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims,
-        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+        3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        mn_major_f32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return check(r, "cuTensorMapEncodeTiled");
 }
 
@@ -311,7 +320,11 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
     // way the reference pads to BLOCK_K = next_power_of_2(D), triton_flash.py:446), causal / full / sliding-window
     // (one- or two-sided) masks.  Everything else (fp32, D % 8 != 0, unaligned pointers) runs the CUDA-core kernels;
     // AULE_LOG=1 reports that choice on stderr.
-    const bool tc = (dtype == kBF16 || dtype == kF16) && (s.D % 8 == 0) && path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0;
+    // fp32 tensors whose caller allows tf32 (dtype code 3): the tensor-core kernel of attn_fwd_tf32_sm100.cu for head_dim <= 64
+    // (P stays fp32 in tensor memory: no room for D = 128); otherwise exactly the fp32 path.
+    const bool tf32 = dtype == kTF32 && s.D <= 64 && path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0;
+    if (dtype == kTF32 && !tf32) dtype = kF32;
+    const bool tc = tf32 || ((dtype == kBF16 || dtype == kF16) && (s.D % 8 == 0) && path_ != kForceCudaCore && ((q | k | v | o) & 15) == 0);
     if (!tc && log_enabled())
         fprintf(stderr, "[aule] forward [%u,%u(%u),%u/%u,%u] %s: CUDA-core kernel (%s)\n", s.B, s.Hq, s.Hkv, s.Sq, s.Sk, s.D,
                 kDtypeSuffix[dtype], path_ == kForceCudaCore ? "forced" : dtype == kF32 ? "fp32 inputs" : (s.D % 8) ? "head_dim % 8 != 0" : "unaligned pointers");
@@ -320,7 +333,7 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         CUtensorMap tmQ, tmK, tmV, tmO;
         if (!(e = make_tmap(&tmQ, dtype, q, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
         if (!(e = make_tmap(&tmK, dtype, k, (uint64_t)s.B * s.Hkv, s.Sk, s.D)).empty()) return e;
-        if (!(e = make_tmap(&tmV, dtype, v, (uint64_t)s.B * s.Hkv, s.Sk, s.D)).empty()) return e;
+        if (!(e = make_tmap(&tmV, dtype, v, (uint64_t)s.B * s.Hkv, s.Sk, s.D, tf32)).empty()) return e;
         if (fwd_v4_ && !(e = make_tmap(&tmO, dtype, o, (uint64_t)s.B * s.Hq, s.Sq, s.D)).empty()) return e;
         FwdParams p;
         p.lse = (float*)lse;
@@ -334,7 +347,7 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
         if (tiles > 0xffffffffull) return "problem too large (work-item count exceeds 2^32)";
         p.num_tiles = (uint32_t)tiles;
         {   // keep ~32 MiB of K/V (two tensors, 16-bit) live per scheduling run so that it stays in the 126 MB L2
-            const uint64_t unit_bytes = 2ull * s.Sk * s.D * 2ull;
+            const uint64_t unit_bytes = 2ull * s.Sk * s.D * (tf32 ? 4ull : 2ull);
             const uint64_t upr = std::max<uint64_t>(1, (32ull << 20) / std::max<uint64_t>(unit_bytes, 1));
             p.units_per_run = (uint32_t)std::min<uint64_t>(upr, (uint64_t)s.B * s.Hkv);
             if (!l2_runs_enabled_) p.units_per_run = s.B * s.Hkv;
@@ -376,6 +389,14 @@ std::string Engine::forward(int dev, CUstream stream, CUdeviceptr q, CUdeviceptr
             return launch_fwd(d.fwd4_sm100[d128 ? 1 : 0], name, grid,
                               d128 ? aule_kp::FwdCfg4<128>::SMEM_BYTES : aule_kp::FwdCfg4<64>::SMEM_BYTES, params4);
         }
+        if (tf32) {
+            // operand-truncation bias of the tf32 MMA, twice in Q K^T (see the kernel's epilogue)
+            p.scale *= 1.00072f;
+            p.scale_log2 *= 1.00072f;
+            if (fwd_v4_ || (path_ >= kVariantBase && path_ < kVariantBase + 16)) return "forward tuning variants are bf16 only";
+            void* params32[] = {&tmQ, &tmK, &tmV, &p};
+            return launch_fwd(d.fwd_tf32, "aule_fwd_sm100_tf32_d64", grid, aule_kp::FwdCfgT32::SMEM_BYTES, params32);
+        }
         const unsigned smem = d128 ? FwdCfg<128>::SMEM_BYTES : FwdCfg<64>::SMEM_BYTES;
         void* params[] = {&tmQ, &tmK, &tmV, &p};
         snprintf(name, sizeof(name), "aule_fwd_sm100_%s_d%u", kDtypeSuffix[dtype], DP);
@@ -411,6 +432,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
     if (!e.empty()) return e;
     if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv) return "null device pointer";
     if (s.Hq > 65535 || s.B > 65535) return "heads/batch exceed the CUDA grid limit (65535)";
+    if (dtype == kTF32) dtype = kF32;                     // the fp32 backward is exact (CUDA cores)
     Device& d = *dp;
     CtxGuard g(drv_, d.ctx);
     if (!(scale > 0.f)) scale = 1.0f / sqrtf((float)s.D);
@@ -807,7 +829,8 @@ std::string Engine::rope(int dev, CUstream stream, CUdeviceptr xq, CUdeviceptr o
     if (!ready_) return "Library not initialized. Call aule_init() first.";
     Device* dp = by_ordinal(dev);
     if (!dp) return "invalid device index";
-    if (dtype < 0 || dtype > 2) return "unsupported dtype (0=f32, 1=bf16, 2=f16)";
+    if (dtype < 0 || dtype > 3) return "unsupported dtype (0=f32, 1=bf16, 2=f16, 3=f32 tensors with tf32 tensor-core math allowed)";
+    if (dtype == kTF32) dtype = kF32;
     if (!xq || !oq || !cos || !sin) return "null device pointer";
     if (bhk && (!xk || !ok)) return "null device pointer";
     if (D == 0 || (D & 1) || !Sq || !bhq) return "RoPE needs an even head_dim and non-empty tensors";

@@ -24,8 +24,10 @@
 
 namespace aule {
 
-enum DType : int32_t { kF32 = 0, kBF16 = 1, kF16 = 2 };
-inline size_t dtype_size(int32_t dt) { return dt == kF32 ? 4 : 2; }
+// kTF32: fp32 tensors in memory, forward allowed to run on the tensor cores as tf32 (head_dim <= 64; otherwise, and in the
+// backward, it behaves exactly like kF32)
+enum DType : int32_t { kF32 = 0, kBF16 = 1, kF16 = 2, kTF32 = 3 };
+inline size_t dtype_size(int32_t dt) { return (dt == kF32 || dt == kTF32) ? 4 : 2; }
 
 struct AttnShape {
     uint32_t B, Hq, Hkv, Sq, Sk, D;
@@ -53,6 +55,7 @@ struct Device {
     CUfunction bwd_delta[3] = {nullptr, nullptr, nullptr};
     CUfunction bwd_dq_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // dQ kernel [dtype][D==128]
     CUfunction bwd_dq1_sm100[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // superseded v1 dQ kernel (tuning builds)
+    CUfunction fwd_tf32 = nullptr;                                  // tf32 forward for fp32 tensors (head_dim <= 64)
     CUfunction bwd_fused_sm100[3] = {nullptr, nullptr, nullptr};   // fused backward (D = 128) [dtype]
     CUfunction bwd_dq_convert[3] = {nullptr, nullptr, nullptr};    // its fp32 dQ accumulator -> 16-bit
     CUfunction rope[3] = {nullptr, nullptr, nullptr};
@@ -175,7 +178,8 @@ private:
     bool host_pinned(const void* p) const;
     std::string launch(Device& d, CUfunction fn, const char* name, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
                        unsigned smem, CUstream stream, void** params);
-    std::string make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D) const;
+    std::string make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D,
+                          bool mn_major_f32 = false) const;
     std::string make_tmap_paged(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint32_t num_blocks, uint32_t block_size,
                                 uint32_t Hkv, uint32_t D) const;
 

@@ -3,6 +3,7 @@
 // src/lib.zig:29-50, and of hipModuleLoadData in src/backends/hip.zig:133-160).
 #include "attn_simt.cu"
 #include "attn_fwd_sm100.cu"
+#include "attn_fwd_tf32_sm100.cu"
 #ifdef AULE_TUNING_VARIANTS
 #include "attn_fwd_sm100_v4.cu"
 #endif

@@ -84,6 +84,30 @@ struct FwdCfg {
     static constexpr int REGS_SOFTMAX = 184, REGS_EPILOGUE = 64, REGS_OTHER = 80;
 };
 
+// tf32 forward (attn_fwd_tf32_sm100.cu): fp32 operands, head_dim <= 64.  An fp32 [128][64] tile has the bytes of a bf16
+// [128][128] one: shared-memory geometry of FwdCfg<128>; P stays fp32 in TMEM (128 columns per tile).
+struct FwdCfgT32 {
+    static constexpr int D = 64;                                // logical (padded) head_dim
+    static constexpr int NS = 4, NQ = 3;
+    static constexpr int CHUNKS = 2;                            // 128-byte swizzle chunks per row: 2 x 32 fp32
+    static constexpr uint32_t CHUNK_BYTES = 128 * 128;
+    static constexpr uint32_t TILE_BYTES = CHUNKS * CHUNK_BYTES;
+    static constexpr uint32_t OFF_Q = 0;
+    static constexpr uint32_t OFF_KV = OFF_Q + NQ * TILE_BYTES;
+    static constexpr bool ROWSUM_MMA = false;
+    static constexpr uint32_t OFF_ONES = OFF_KV + NS * TILE_BYTES;
+    static constexpr uint32_t OFF_STAT = OFF_ONES;
+    static constexpr uint32_t OFF_WORK = OFF_STAT + 4 * 128 * 4;
+    static constexpr uint32_t OFF_BAR = OFF_WORK + 8 * 32;
+    static constexpr int NBAR = 39 + 2 * NS;
+    static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + NBAR * 8;
+    static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+    static constexpr uint32_t COL_S = 0, COL_P0 = 128, COL_P1 = 256, COL_O0 = 384, COL_O1 = 448;
+    static constexpr uint32_t PV_N = D;
+    static constexpr int REGS_SOFTMAX = 184, REGS_EPILOGUE = 64, REGS_OTHER = 80;
+};
+
 // v4 layout (attn_fwd_sm100_v4.cu, tuning builds only): Q 2 tiles | K/V ring (4 x [128 keys][D], K and V tiles interleaved) | one O staging
 // tile | row statistics | mbarriers.  TMEM: one shared S buffer, P0, P1, O0, O1.
 template <int D>

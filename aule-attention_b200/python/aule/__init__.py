@@ -85,6 +85,10 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
             |i-j| <= W//2 (the shader's convention, attention_f32.comp:173-183).  The reference's generic Triton
             kernel keeps i-j <= W / |i-j| <= W (triton_flash.py:190-194): its W is W+1 (causal) / 2W (bidirectional) here.
 
+    fp32 CUDA tensors run exact fp32 arithmetic (CUDA cores) unless tf32 is allowed -- aule.set_fp32_tf32(True) or AULE_TF32=1 --
+    in which case head_dim <= 64 runs the forward on the tensor cores as tf32 (~1e-3 relative error), which is what the
+    reference's Triton path always does with fp32 inputs (tl.dot, triton_flash.py:405-411).
+
     Returns: tensor with the shape (and dtype/device kind) of `query`.
     Raises: ValueError for invalid shapes; RuntimeError if no B200 backend is available.
     """
@@ -143,6 +147,13 @@ def flash_attention(query, key, value, rot_cos=None, rot_sin=None, causal=True, 
 attention = flash_attention      # alias, __init__.py:275
 
 
+def set_fp32_tf32(allow):
+    """(extension) True: fp32 CUDA tensors may run the forward as tf32 on the tensor cores (head_dim <= 64); False: always exact
+    fp32; None: follow the AULE_TF32 environment variable (the default)."""
+    from . import cuda_flash
+    cuda_flash._tf32_override = None if allow is None else bool(allow)
+
+
 def flash_attention_rope(q, k, v, cos, sin, causal=True, scale=None, window_size=-1, interleaved=False):
     """RoPE on Q and K, then attention -- reference: triton_flash.py:561-603 (half-split convention, the default);
     interleaved=True selects the Vulkan shader's adjacent-pair convention (attention_f32.comp:98-111)."""
@@ -190,9 +201,14 @@ def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.
     import torch
     # Only shapes the tensor-core kernel takes are routed here (16-bit, head_dim <= 128 and a multiple of 8): anything
     # that would land on the CUDA-core kernels (fp32, other head_dims) is SLOWER than the SDPA it would replace.
+    # fp32: only when torch itself is allowed to use tf32 for fp32 matmuls, for shapes the tf32 kernel takes, and not for training
+    # (the fp32 backward is the exact CUDA-core one)
+    tf32_ok = (query.dtype == torch.float32 and torch.backends.cuda.matmul.allow_tf32 and query.dim() == 4
+               and query.shape[-1] <= 64 and query.shape[-1] % 4 == 0
+               and not (torch.is_grad_enabled() and (query.requires_grad or key.requires_grad or value.requires_grad)))
     needs_fallback = (attn_mask is not None or dropout_p > 0.0 or not _cuda_available or not query.is_cuda
-                      or query.dim() != 4 or query.shape[-1] > 128 or query.shape[-1] % 8 != 0
-                      or query.dtype not in (torch.bfloat16, torch.float16)
+                      or query.dim() != 4 or query.shape[-1] > 128 or (query.shape[-1] % 8 != 0 and not tf32_ok)
+                      or (query.dtype not in (torch.bfloat16, torch.float16) and not tf32_ok)
                       or key.dtype != query.dtype or value.dtype != query.dtype
                       or (is_causal and query.shape[-2] != key.shape[-2])      # SDPA's causal is top-left too, but be strict
                       or (query.shape[1] != key.shape[1] and not enable_gqa))
@@ -202,6 +218,9 @@ def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.
             raise RuntimeError("no original SDPA available for fallback")
         return fn(query, key, value, attn_mask=attn_mask, dropout_p=dropout_p, is_causal=is_causal, scale=scale,
                   enable_gqa=enable_gqa)
+    if tf32_ok:
+        from . import cuda_flash
+        return cuda_flash.flash_attention_cuda(query, key, value, causal=is_causal, scale=scale, allow_tf32=True)
     return flash_attention(query, key, value, causal=is_causal, scale=scale)
 
 

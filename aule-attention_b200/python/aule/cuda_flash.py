@@ -26,7 +26,7 @@ class FlashAttentionCudaFunc(torch.autograd.Function):
     """Autograd wrapper (mirror of triton_flash.py:386-526)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, causal, scale, window_size):
+    def forward(ctx, q, k, v, causal, scale, window_size, allow_tf32=False):
         lib = ffi.ensure_init()
         B, Hq, Sq, D = q.shape
         _, Hkv, Sk, _ = k.shape
@@ -39,8 +39,9 @@ class FlashAttentionCudaFunc(torch.autograd.Function):
         lse = torch.empty((B, Hq, Sq), device=q.device, dtype=torch.float32)   # :437
         dev = q.device.index if q.device.index is not None else torch.cuda.current_device()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        code = ffi.DTYPE_F32_TF32 if (allow_tf32 and cdt == torch.float32) else _TORCH_TO_AULE[cdt]
         rc = lib.aule_attention_forward_dptr(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
-                                             B, Hq, Hkv, Sq, Sk, D, _TORCH_TO_AULE[cdt], float(scale),
+                                             B, Hq, Hkv, Sq, Sk, D, code, float(scale),
                                              1 if causal else 0, int(window_size), dev, stream)
         _check(rc, "Attention failed")
         ctx.save_for_backward(q, k, v, out, lse)                         # :466
@@ -71,15 +72,29 @@ class FlashAttentionCudaFunc(torch.autograd.Function):
                                                   1 if ctx.causal else 0, dev, stream)
         _check(rc, "Backward pass failed")
         od = ctx.orig_dtype
-        return dq.to(od), dk.to(od), dv.to(od), None, None, None         # :526
+        return dq.to(od), dk.to(od), dv.to(od), None, None, None, None   # :526
 
 
-def flash_attention_cuda(q, k, v, causal=True, scale=None, window_size=-1):
+_tf32_override = None      # aule.set_fp32_tf32()
+
+
+def tf32_allowed(allow_tf32=None):
+    """fp32 inputs: exact fp32 arithmetic unless tf32 is allowed (argument, aule.set_fp32_tf32, or AULE_TF32=1 in the environment).
+    The reference's Triton path always runs fp32 inputs as tf32 (tl.dot default); its Vulkan shaders are exact."""
+    import os
+    if allow_tf32 is not None:
+        return bool(allow_tf32)
+    if _tf32_override is not None:
+        return _tf32_override
+    return os.environ.get("AULE_TF32", "0") == "1"
+
+
+def flash_attention_cuda(q, k, v, causal=True, scale=None, window_size=-1, allow_tf32=None):
     """Mirror of flash_attention_triton (triton_flash.py:529-558)."""
-    return FlashAttentionCudaFunc.apply(q, k, v, causal, scale, window_size)
+    return FlashAttentionCudaFunc.apply(q, k, v, causal, scale, window_size, tf32_allowed(allow_tf32))
 
 
-def forward_with_lse(q, k, v, causal=True, scale=None, window_size=-1):
+def forward_with_lse(q, k, v, causal=True, scale=None, window_size=-1, allow_tf32=None):
     """Forward that also returns LSE [B,Hq,Sq] (fp32) -- no autograd."""
     lib = ffi.ensure_init()
     B, Hq, Sq, D = q.shape
@@ -89,8 +104,9 @@ def forward_with_lse(q, k, v, causal=True, scale=None, window_size=-1):
     out = torch.empty_like(q)
     lse = torch.empty((B, Hq, Sq), device=q.device, dtype=torch.float32)
     dev = q.device.index if q.device.index is not None else torch.cuda.current_device()
+    code = ffi.DTYPE_F32_TF32 if (cdt == torch.float32 and tf32_allowed(allow_tf32)) else _TORCH_TO_AULE[cdt]
     rc = lib.aule_attention_forward_dptr(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(),
-                                         B, Hq, Hkv, Sq, Sk, D, _TORCH_TO_AULE[cdt],
+                                         B, Hq, Hkv, Sq, Sk, D, code,
                                          float(scale) if scale else 0.0, 1 if causal else 0, int(window_size), dev,
                                          torch.cuda.current_stream(dev).cuda_stream)
     _check(rc, "Attention failed")

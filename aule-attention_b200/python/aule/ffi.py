@@ -20,6 +20,7 @@ _INITIALIZED = False
 _INIT_ERROR = None
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+DTYPE_F32_TF32 = 3      # fp32 tensors, forward allowed to use tf32 tensor-core math (head_dim <= 64)
 
 
 class AuleError(Exception):

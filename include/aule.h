@@ -128,7 +128,11 @@ AULE_API int32_t aule_attention_forward_gravity(uint64_t q, uint64_t k, uint64_t
 /* fills with Triton: FlashAttentionTritonFunc, triton_flash.py:386-526)     */
 /* ------------------------------------------------------------------------ */
 
-enum { AULE_DTYPE_F32 = 0, AULE_DTYPE_BF16 = 1, AULE_DTYPE_F16 = 2 };
+/* AULE_DTYPE_F32_TF32: fp32 tensors in memory whose forward MAY run on the tensor cores as tf32 -- what the reference's GPU
+ * path does with fp32 inputs (tl.dot on fp32 operands, triton_flash.py:405-411, Triton's default allow_tf32); taken for
+ * head_dim <= 64 (error <= 1e-3 relative to the output scale), exactly AULE_DTYPE_F32 everywhere else and in every backward.
+ * AULE_DTYPE_F32 itself is always exact fp32 arithmetic (the Vulkan shaders' behaviour, attention_f32.comp). */
+enum { AULE_DTYPE_F32 = 0, AULE_DTYPE_BF16 = 1, AULE_DTYPE_F16 = 2, AULE_DTYPE_F32_TF32 = 3 };
 
 /* Fused forward on raw device pointers (CUdeviceptr), asynchronous on
  * `cu_stream` of `device` (no implicit sync).
@@ -140,8 +144,8 @@ enum { AULE_DTYPE_F32 = 0, AULE_DTYPE_BF16 = 1, AULE_DTYPE_F16 = 2 };
  *                  i-j <= W, |i-j| <= W) is W+1 causal / 2W bidirectional here)
  *   GQA         => kv_head = q_head / (Hq/Hkv)          (triton_flash.py:95-96)
  * bf16/fp16 with D <= 128, D % 8 == 0 run the tcgen05/TMA kernel (D is zero-padded to 64 / 128 by the TMA boxes,
- * like BLOCK_K = next_power_of_2(D) in triton_flash.py:446); fp32 and D % 8 != 0 run the fp32-accumulate CUDA-core
- * kernel (AULE_LOG=1 reports that choice on stderr).
+ * like BLOCK_K = next_power_of_2(D) in triton_flash.py:446); AULE_DTYPE_F32_TF32 with D <= 64 runs the kind::tf32 variant of
+ * the same kernel; fp32 and D % 8 != 0 run the fp32-accumulate CUDA-core kernel (AULE_LOG=1 reports that choice on stderr).
  * Replaces _flash_attn_fwd_kernel launch, triton_flash.py:448-464. */
 AULE_API int32_t aule_attention_forward_dptr(uint64_t q, uint64_t k, uint64_t v, uint64_t o,
                                              uint64_t lse_or_0, uint32_t B, uint32_t Hq, uint32_t Hkv,

@@ -188,6 +188,66 @@ def test_padded_head_dim_backward_on_tensor_cores(aule, D, dtype, B, Hq, Hkv, Sq
         assert orc.rel_err_to_scale(g, e_) <= BF16_TOL, orc.rel_err_to_scale(g, e_)
 
 
+# ------------------------------------------------------------------ fp32 inputs on the tensor cores (tf32)
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,D,causal,window", [
+    (2, 8, 8, 512, 512, 64, True, -1),          # config A's shape class (fp32 causal MHA, D = 64)
+    (4, 32, 32, 2048, 2048, 64, True, -1),      # fp32 [4,32,2048,64] within 1e-3
+    (1, 8, 2, 300, 300, 64, True, -1),          # GQA, ragged
+    (1, 4, 4, 200, 333, 32, False, -1),         # padded head dim, cross attention
+    (1, 2, 1, 130, 700, 40, False, -1),
+    (1, 4, 2, 384, 384, 64, True, 100),         # causal window
+    (1, 2, 2, 300, 500, 48, False, 64),         # bidirectional window, padded
+    (1, 2, 2, 700, 200, 64, False, 2),          # rows without a visible key
+])
+def test_fp32_inputs_tf32_tensor_core_forward(aule, B, Hq, Hkv, Sq, Sk, D, causal, window):
+    """The reference's GPU path runs fp32 inputs through tl.dot, i.e. as tf32 (triton_flash.py:405-411).  With tf32 allowed the
+    fp32 forward runs the kind::tf32 tcgen05 kernel (head_dim <= 64): error <= 1e-3 relative to the output scale (north_star's
+    fp32 bar) against the fp64 oracle; without it the exact CUDA-core kernel runs."""
+    import torch
+    from aule import cuda_flash, ffi
+    lib = ffi.load_library()
+    q, k, v = ref_inputs(B, Hq, Sq, D, Hkv=Hkv, Sk=Sk)
+    tq, tk, tv = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (q, k, v))
+    out, lse = cuda_flash.forward_with_lse(tq, tk, tv, causal=causal, window_size=window, allow_tf32=True)
+    torch.cuda.synchronize()
+    assert lib.aule_last_kernel().decode() == "aule_fwd_sm100_tf32_d64"
+    if B * Hq * Sq * Sk <= 1 << 28:
+        exp, exp_lse = orc.attention_ref(q, k, v, causal=causal, window=window)
+    else:                                                       # full-size case: the exact fp32 kernel is the yardstick
+        e32, l32 = cuda_flash.forward_with_lse(tq, tk, tv, causal=causal, window_size=window, allow_tf32=False)
+        assert lib.aule_last_kernel().decode() == "aule_fwd_simt_f32"
+        exp, exp_lse = e32.cpu().numpy(), l32.cpu().numpy()
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all()
+    live = np.isfinite(exp_lse)                                  # rows without a visible key: O = 0, LSE = -inf (the oracle has NaN there)
+    assert (o[~live] == 0).all()
+    assert orc.rel_err_to_scale(o[live], exp[live]) <= FP32_TOL, orc.rel_err_to_scale(o[live], exp[live])
+    assert (np.isneginf(lse.cpu().numpy()) == ~live).all()
+    np.testing.assert_allclose(lse.cpu().numpy()[live], exp_lse[live], rtol=2e-3, atol=2e-3)
+
+
+def test_fp32_tf32_is_opt_in(aule):
+    """fp32 tensors stay on the exact fp32 kernel unless tf32 is allowed (aule.set_fp32_tf32 / AULE_TF32); head_dim > 64 always does."""
+    import torch
+    from aule import ffi
+    lib = ffi.load_library()
+    q = torch.randn(1, 4, 256, 64, device="cuda")
+    aule.flash_attention(q, q, q, causal=True)
+    assert lib.aule_last_kernel().decode() == "aule_fwd_simt_f32"
+    aule.set_fp32_tf32(True)
+    try:
+        o = aule.flash_attention(q, q, q, causal=True)
+        assert lib.aule_last_kernel().decode() == "aule_fwd_sm100_tf32_d64" and o.dtype == torch.float32
+        q128 = torch.randn(1, 2, 256, 128, device="cuda")
+        aule.flash_attention(q128, q128, q128, causal=True)
+        assert lib.aule_last_kernel().decode() == "aule_fwd_simt_f32"
+        qg = q.clone().requires_grad_()                        # training: tf32 forward, exact fp32 backward
+        aule.flash_attention(qg, qg, qg, causal=True).sum().backward()
+        assert torch.isfinite(qg.grad).all()
+    finally:
+        aule.set_fp32_tf32(None)
+
+
 # ------------------------------------------------------------------ fused backward (opt-in)
 @pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,causal,dtype", [
     (1, 2, 1, 256, 256, True, "bf16"), (2, 4, 2, 1000, 1000, True, "f16"), (1, 2, 1, 300, 520, False, "bf16"), (1, 8, 2, 1536, 1536, True, "bf16")])
