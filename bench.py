@@ -433,6 +433,47 @@ def main():
         t_ = bwd_block("config_C_half_bwd", 4, 32, 8, 4096, 128, sec_steps)
         del t_
         torch.cuda.empty_cache()
+        t_ = bwd_block("config_B_bwd", 4, 32, 32, 2048, 64, sec_steps)
+        del t_
+        torch.cuda.empty_cache()
+        # tensor-core backward outside the (64, 128) x (causal, full) grid: a padded head dim and a sliding window
+        t_ = bwd_block("padded_D96_bwd", 4, 32, 8, 4096, 96, sec_steps)
+        secondary["padded_D96_bwd"]["note"] = "head_dim 96 runs the D = 128 kernels (TMA zero-fills / clips the padding): FLOPs counted at D = 96"
+        del t_
+        torch.cuda.empty_cache()
+
+        # fp32 inputs: tf32 tensor-core forward (opt-in) against the exact CUDA-core fp32 kernel and torch SDPA
+        try:
+            Bt, Ht, St, Dt = 4, 32, 2048, 64
+            gt = torch.Generator(device=dev).manual_seed(5)
+            qt_, kt_, vt_ = (torch.randn(Bt, Ht, St, Dt, device=dev, generator=gt) for _ in range(3))
+            ot_ = torch.empty_like(qt_); lt_ = torch.empty(Bt, Ht, St, device=dev, dtype=torch.float32)
+
+            def f32_call(code):
+                rc = lib.aule_attention_forward_dptr(qt_.data_ptr(), kt_.data_ptr(), vt_.data_ptr(), ot_.data_ptr(), lt_.data_ptr(),
+                                                     Bt, Ht, Ht, St, St, Dt, code, 0.0, 1, -1, local_rank, stream.cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(ffi.last_error())
+            flt = causal_flops(Bt, Ht, St, Dt)
+            ms_t = time_events(lambda: f32_call(3), 30, 5)
+            kern_t = lib.aule_last_kernel().decode()
+            o_tf32 = ot_.clone()
+            ms_x = time_events(lambda: f32_call(0), 3, 1)
+            err = ((o_tf32 - ot_).abs().max() / ot_.abs().max()).item()
+            secondary["fp32_tf32_fwd"] = {"shape": [Bt, Ht, Ht, St, Dt], "dtype": "fp32 tensors, tf32 tensor-core math (dtype code 3)", "ms": ms_t,
+                                          "tflops": flt / ms_t / 1e9, "kernel": kern_t, "exact_fp32_cuda_core_ms": ms_x,
+                                          "exact_fp32_cuda_core_tflops": flt / ms_x / 1e9, "max_err_vs_exact_rel_to_scale": err}
+            try:
+                import torch.nn.functional as F
+                torch.backends.cuda.matmul.allow_tf32 = True
+                msy = time_events(lambda: F.scaled_dot_product_attention(qt_, kt_, vt_, is_causal=True), 10, 3)
+                secondary["fp32_tf32_fwd"]["torch_sdpa_fp32_tflops"] = flt / msy / 1e9
+            except Exception as ex:
+                secondary["fp32_tf32_fwd"]["torch_sdpa_fp32_tflops"] = f"unavailable: {type(ex).__name__}"
+            del qt_, kt_, vt_, ot_, lt_, o_tf32
+        except Exception as ex:
+            secondary["fp32_tf32_fwd"] = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
         qe, ke, ve, oe, le, doe = bwd_block("config_E_fwd_bwd", 2, 16, 16, 1024, 64, 50)
         # config E end to end from pinned host buffers: forward (+LSE) then backward, all copies inside
         hs = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (qe, ke, ve, oe, doe, le)]
