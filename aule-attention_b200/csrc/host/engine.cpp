@@ -462,7 +462,9 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             uint32_t D = s.D;
             void* params[] = {&o, &d_o, &delta, &rows, &D};
             snprintf(name, sizeof(name), "aule_bwd_delta_%s", kDtypeSuffix[dtype]);
-            e = launch(d, d.bwd_delta[dtype], name, (unsigned)((rows + 7) / 8), 1, 1, 256, 0, stream, params);
+            // 256 threads = 8 warps; a warp covers (32 / lanes-per-row) rows x 4 rows in flight (delta_body)
+            const uint64_t rows_per_cta = 8ull * (32u / (s.D <= 32 ? 4u : (s.D <= 64 ? 8u : 16u))) * 4ull;
+            e = launch(d, d.bwd_delta[dtype], name, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta), 1, 1, 256, 0, stream, params);
         }
         std::lock_guard<std::mutex> launch_guard(launch_mu_[d.index]);   // s_aux and the fork / join events are per device
         if (e.empty() && bwd_two_streams_) e = check(drv_.cuEventRecord(d.ev_fork, stream), "cuEventRecord");

@@ -455,11 +455,14 @@ __device__ __forceinline__ void bwd_fused_body(const CUtensorMap* tmQ, const CUt
             tma_store_3d(tmdK, sdO0 + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
         }
         tma_store_commit();
-        tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 16) tmem_dealloc<512>(tmem);
+    // The CTA only has to outlive the TMA engine's READ of its shared memory; the global writes complete on their own
+    // (kernel completion orders them).  Waiting for the writes held every CTA ~1 us past its last useful cycle -- with 8.5
+    // steps per CTA on config B that is paid 14 times per SM.
+    if (threadIdx.x == 0) tma_store_wait_read<0>();
 }
 
 // fp32 dQ accumulator -> 16-bit (x scale): 8 elements per thread and iteration

@@ -860,11 +860,14 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             tma_store_3d(tmdK, sdO0 + c * C::CHUNK_BYTES, c * 64, (int32_t)key0, (int32_t)bhk);
         }
         tma_store_commit();
-        tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 16) tmem_dealloc<512>(tmem);
+    // The CTA only has to outlive the TMA engine's READ of its shared memory; the global writes complete on their own
+    // (kernel completion orders them).  Waiting for the writes held every CTA ~1 us past its last useful cycle -- with 8.5
+    // steps per CTA on config B that is paid 14 times per SM.
+    if (threadIdx.x == 0) tma_store_wait_read<0>();
 }
 
 // =====================================================================================================
@@ -1500,25 +1503,60 @@ AULE_BWD100_DQ(aule_bwd_dq1_sm100_f16_d128, 128, false)
 AULE_BWD100_DQ(aule_bwd_dq1_sm100_f16_d64, 64, false)
 #endif
 
-// Delta_i = sum_d O_id dO_id (triton_flash.py:353-379), one warp per row.
-template <typename T>
-__device__ __forceinline__ void delta_body(const T* o, const T* d_o, float* delta, uint64_t rows, uint32_t D) {
-    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const uint32_t lane = threadIdx.x & 31;
+// Delta_i = sum_d O_id dO_id (triton_flash.py:353-379).  HBM-bound (reads O and dO once: 4*D bytes per row at 16 bits):
+// a thread owns 8 consecutive elements (one 16-byte load per tensor) of a row, L = 4 / 8 / 16 lanes share a row (D <= 32 /
+// 64 / 128; D % 8 == 0 and 16-byte aligned pointers on this path), and every thread keeps 4 rows in flight (8 independent
+// 16-byte loads) before it reduces -- the round-1 kernel (a warp per row, 4-byte loads) ran at 2-3.8 TB/s.
+template <bool BF16>
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
     float acc = 0.f;
-    for (uint32_t d = lane * 2; d < D; d += 64) {
-        const float2 a = make_float2((float)o[row * D + d], (float)o[row * D + d + 1]);
-        const float2 g = make_float2((float)d_o[row * D + d], (float)d_o[row * D + d + 1]);
-        acc = fmaf(a.x, g.x, fmaf(a.y, g.y, acc));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 x, y;
+        if constexpr (BF16) {
+            x = make_float2(__uint_as_float(aw[i] << 16), __uint_as_float(aw[i] & 0xffff0000u));
+            y = make_float2(__uint_as_float(bw[i] << 16), __uint_as_float(bw[i] & 0xffff0000u));
+        } else {
+            x = __half22float2(*reinterpret_cast<const __half2*>(&aw[i]));
+            y = __half22float2(*reinterpret_cast<const __half2*>(&bw[i]));
+        }
+        acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+    }
+    return acc;
+}
+template <typename T, bool BF16>
+__device__ __forceinline__ void delta_body(const T* o, const T* d_o, float* delta, uint64_t rows, uint32_t D) {
+    constexpr int R = 4;                                            // rows in flight per thread
+    const uint32_t L = D <= 32 ? 4u : (D <= 64 ? 8u : 16u);          // lanes per row
+    const uint32_t rpw = 32u / L;                                    // rows per warp and pass
+    const uint32_t lane = threadIdx.x & 31, sub = lane % L, rl = lane / L;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t row0 = warp * (uint64_t)(rpw * R) + rl;           // this thread's rows: row0 + i * rpw
+    const bool col_ok = sub * 8 < D;
+    uint4 a[R], b[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const uint64_t row = row0 + (uint64_t)i * rpw;
+        a[i] = b[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows && col_ok) {
+            a[i] = __ldg(reinterpret_cast<const uint4*>(o + row * D + sub * 8));
+            b[i] = __ldg(reinterpret_cast<const uint4*>(d_o + row * D + sub * 8));
+        }
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) delta[row] = acc;
+    for (int i = 0; i < R; ++i) {
+        float acc = dot8<BF16>(a[i], b[i]);
+#pragma unroll
+        for (int s = 8; s > 0; s >>= 1)
+            if ((uint32_t)s < L) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        const uint64_t row = row0 + (uint64_t)i * rpw;
+        if (sub == 0 && row < rows) delta[row] = acc;
+    }
 }
-extern "C" __global__ void aule_bwd_delta_bf16(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta, uint64_t rows, uint32_t D) {
-    delta_body(o, d_o, delta, rows, D);
+extern "C" __global__ void __launch_bounds__(256) aule_bwd_delta_bf16(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta, uint64_t rows, uint32_t D) {
+    delta_body<__nv_bfloat16, true>(o, d_o, delta, rows, D);
 }
-extern "C" __global__ void aule_bwd_delta_f16(const __half* o, const __half* d_o, float* delta, uint64_t rows, uint32_t D) {
-    delta_body(o, d_o, delta, rows, D);
+extern "C" __global__ void __launch_bounds__(256) aule_bwd_delta_f16(const __half* o, const __half* d_o, float* delta, uint64_t rows, uint32_t D) {
+    delta_body<__half, false>(o, d_o, delta, rows, D);
 }
