@@ -161,8 +161,9 @@ public:
     //   bits 18-22 backward, fused kernel: (batch, kv-head) units per CTA run (0 = default)
     //   bit 23     backward: the v1 dQ kernel (tuning builds only; an error otherwise)
     //   bit 24     backward dK/dV kernel: try_wait side polls in the issuer's load pump (the pre-round-2 behaviour; A/B)
+    //   bit 25     backward dK/dV kernel, head_dim <= 64: one S^T buffer instead of two (the earlier behaviour; A/B)
     void set_kernel_path(int32_t p) {
-        bwd_fused_ = (p >> 17) & 1; bwd_units_per_run_ = (p >> 18) & 31; bwd_dq_v1_ = (p >> 23) & 1; bwd_legacy_poll_ = (p >> 24) & 1;
+        bwd_fused_ = (p >> 17) & 1; bwd_units_per_run_ = (p >> 18) & 31; bwd_dq_v1_ = (p >> 23) & 1; bwd_legacy_poll_ = (p >> 24) & 1; bwd_single_s_ = (p >> 25) & 1;
         pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; bwd_two_streams_ = !(p & 65536); path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
@@ -196,6 +197,7 @@ private:
     int32_t bwd_fused_ = 0;
     int32_t bwd_dq_v1_ = 0;
     int32_t bwd_legacy_poll_ = 0;
+    int32_t bwd_single_s_ = 0;
     int32_t bwd_units_per_run_ = 0;
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)

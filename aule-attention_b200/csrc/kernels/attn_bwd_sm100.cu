@@ -503,10 +503,11 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
     const uint32_t bar_ds = bar_p + 8;                  // compute -> issuer: dS^T(i) in TMEM (16 arrivals)
     const uint32_t bar_done = bar_ds + 8;               // every MMA complete (commit)
     const uint32_t bar_pb = bar_done + 24;              // compute -> issuer: second half of P^T(i) (bar_p announces the first half)
+    const uint32_t bar_s1 = bar_done + 32;              // S^T(i) complete, odd steps (D = 64: second S^T buffer, one barrier per buffer)
     const uint32_t bar_stat0 = bar_done + 8;            // publishers -> everyone: statistics of step s are in buffer s&1 (4 arrivals);
                                                         // one barrier per buffer, so a waiter can never be lapped (the next
                                                         // completion of ITS barrier needs its own dS^T arrival two steps on)
-    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 8) <= C::BAR_BYTES, "barrier area too small");
+    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 9) <= C::BAR_BYTES, "barrier area too small");
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
     float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [3][lse2 x128 | delta x128]
     const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO;
@@ -517,7 +518,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
         for (int i = 0; i < NQ; ++i) { mbar_init(bar_qfull0 + 8 * i, 1); mbar_init(bar_qfree0 + 8 * i, 1); }
         for (int i = 0; i < NDO; ++i) { mbar_init(bar_dofull0 + 8 * i, 1); mbar_init(bar_dofree0 + 8 * i, 1); }
         mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_done, 1);
-        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4); mbar_init(bar_pb, 16);
+        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4); mbar_init(bar_pb, 16); mbar_init(bar_s1, 1);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
@@ -526,7 +527,13 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 384;
+    // TMEM: S^T [0,128) | dP^T [128,256) | dV [256,256+D) | dK.  D = 128 fills the 512 columns; D = 64 leaves 128, which hold a
+    // SECOND S^T buffer [384,512): S^T(i+1) then no longer has to wait behind dV(i) for the columns P^T(i) occupies, it is
+    // issued at the top of step i and is complete long before the compute warps finish dS^T(i).  (Trace of config B before:
+    // ~600 of the ~2950 cycles per step were the compute warps waiting for S^T(i+1), whose issue waited for every warp's
+    // P^T(i); BwdParams::order bit 3 keeps the single buffer for A/B.)
+    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = (D == 64) ? 320 : 384, COL_S1 = 384;
+    const bool two_s = (D == 64) && !(p.order & 8);
 
     // ---- which KV block
     const uint32_t per = p.Hkv * p.B;
@@ -585,14 +592,15 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             auto wait = [&](uint32_t bar, uint32_t parity) {                 // blocking wait that keeps the loads flowing
                 while (!mbar_try_wait<0>(bar, parity)) pump();
             };
-            auto issue_s = [&](uint32_t qst) {                               // S^T = K_j Q^T  (A = K_j, B = Q as [n = query][k = d])
+            auto issue_s = [&](uint32_t qst, uint32_t buf) {                 // S^T = K_j Q^T  (A = K_j, B = Q as [n = query][k = d])
                 const uint32_t sQ = sQ0 + qst * C::TILE_BYTES;
+                const uint32_t col = buf ? COL_S1 : COL_S;
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t off = ((kk / 4) * C::CHUNK_BYTES + (kk % 4) * 32) >> 4;
-                    mma_ss(tmem + COL_S, mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sQ >> 4)) + off), ID_KK, kk > 0);
+                    mma_ss(tmem + col, mk(HI_K_HI, (HI_K_LO | (sK >> 4)) + off), mk(HI_K_HI, (HI_K_LO | (sQ >> 4)) + off), ID_KK, kk > 0);
                 }
-                mma_commit(bar_s);
+                mma_commit(buf ? bar_s1 : bar_s);
             };
             auto issue_dp = [&](uint32_t dst_) {                             // dP^T = V_j dO^T
                 const uint32_t sdO = sdO0 + dst_ * C::TILE_BYTES;
@@ -613,7 +621,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             wait(bar_kv, 0);
             wait(bar_qfull0, 0);
             tc_fence_after();
-            issue_s(0);
+            issue_s(0, 0);
             wait(bar_dofull0, 0);
             tc_fence_after();
             issue_dp(0);
@@ -625,6 +633,15 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 // dV += P^T dO (K = 128 queries, A = P^T in TMEM), in two halves: every thread publishes the first 16 of its
                 // 32 query columns (the even k-steps) before it computes the other 16, so half of dV runs under that math
                 // instead of after it -- dV gates S^T(step+1), the head of the next step's chain.
+                const uint32_t colS = (two_s && (step & 1)) ? COL_S1 : COL_S;      // where S^T(step) / P^T(step) live
+                if (two_s && step + 1 < nsteps) {
+                    // second buffer: its previous tenant P^T(step-1) was read by dV(step-1), issued one iteration ago and
+                    // ahead of this in the in-order tensor pipe; every warp stored that P^T before bar_pb(step-1) completed
+                    wait(bar_qfull0 + 8 * qs_next, qp_next);
+                    tr.ev(14, step);
+                    tc_fence_after();
+                    issue_s(qs_next, (step + 1) & 1);
+                }
                 {
                     const uint32_t sdO = sdO0 + ds_ * C::TILE_BYTES;
                     tr.ev(17, step);
@@ -633,21 +650,21 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 8; kk += 2)
-                        mma_ts(tmem + COL_DV, tmem + COL_S + 32 * (kk >> 1) + 8 * (kk & 1),
+                        mma_ts(tmem + COL_DV, tmem + colS + 32 * (kk >> 1) + 8 * (kk & 1),
                                mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128), ID_KMN, (step > 0 || kk > 0) ? 1u : 0u);
                     wait(bar_pb, step & 1);                                  // second halves
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 1; kk < 8; kk += 2)
-                        mma_ts(tmem + COL_DV, tmem + COL_S + 32 * (kk >> 1) + 8 * (kk & 1),
+                        mma_ts(tmem + COL_DV, tmem + colS + 32 * (kk >> 1) + 8 * (kk & 1),
                                mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128), ID_KMN, 1u);
                     mma_commit(bar_dofree0 + 8 * ds_);
                 }
-                if (step + 1 < nsteps) {
+                if (!two_s && step + 1 < nsteps) {
                     wait(bar_qfull0 + 8 * qs_next, qp_next);
                     tr.ev(14, step);
                     tc_fence_after();
-                    issue_s(qs_next);                                        // overwrites P^T(step): after dV(step) in the pipe
+                    issue_s(qs_next, 0);                                     // overwrites P^T(step): after dV(step) in the pipe
                 }
                 wait(bar_ds, step & 1);                                      // dS^T(step) in TMEM
                 tr.ev(13, step);
@@ -728,12 +745,14 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
             // ---- P phase: P^T = exp2(S^T*scale_log2 - lse2[query]) -> 16-bit, in place over the first 16 columns
             float pv[32];
             tr.ev(20, step);
-            mbar_wait(bar_s, step & 1);
+            const bool odd_buf = two_s && (step & 1);                // S^T(step) / P^T(step) in the second buffer
+            const uint32_t tSs = tS + (odd_buf ? COL_S1 : 0u);
+            mbar_wait(odd_buf ? bar_s1 : bar_s, two_s ? ((step >> 1) & 1) : (step & 1));
             tr.ev(21, step);
             tc_fence_after();
             {
                 uint32_t s[32];
-                tmem_ld32(tS, s);
+                tmem_ld32(tSs, s);
                 tmem_wait_ld();
                 tr.ev(22, step);
                 const float2 cc = make_float2(p.scale_log2, p.scale_log2);
@@ -775,7 +794,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     uint32_t pk[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) pk[e] = pack2<BF16>(pv[16 * half + 2 * e], pv[16 * half + 2 * e + 1]);
-                    tmem_st8(tS + 8 * half, pk);
+                    tmem_st8(tSs + 8 * half, pk);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();

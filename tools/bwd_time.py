@@ -12,15 +12,20 @@ from aule import cuda_flash, ffi  # noqa: E402
 
 lib = ffi.ensure_init()
 stream = torch.cuda.current_stream().cuda_stream
-out = {"lib": os.environ.get("AULE_LIBRARY_PATH", "default")}
+path = int(os.environ.get("AULE_PATH", "0"))
+lib.aule_set_kernel_path(path)
+out = {"lib": os.environ.get("AULE_LIBRARY_PATH", "default"), "path": path}
+shapes = os.environ.get("AULE_SHAPES", "C_half,B,E,D96").split(",")
 for name, (B, Hq, Hkv, S, D), reps in (("C_half", (4, 32, 8, 4096, 128), 15), ("B", (4, 32, 32, 2048, 64), 30), ("E", (2, 16, 16, 1024, 64), 100),
-                                       ("D96", (4, 32, 8, 4096, 96), 10)):
+                                       ("D96", (4, 32, 8, 4096, 96), 10), ("B_gqa", (4, 32, 8, 2048, 64), 30), ("B_long", (1, 32, 32, 8192, 64), 15)):
+    if name not in shapes:
+        continue
     g = torch.Generator(device="cuda").manual_seed(1)
     q = torch.randn(B, Hq, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
     k = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
     v = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
     o, lse = cuda_flash.forward_with_lse(q, k, v, causal=True)
-    do = torch.randn_like(o)
+    do = torch.randn(o.shape, device="cuda", dtype=torch.bfloat16, generator=g)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
 
     def call():

@@ -16,7 +16,7 @@ lib = ffi.ensure_init()
 which = sys.argv[1] if len(sys.argv) > 1 else "dq"
 lo = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 hi = int(sys.argv[3]) if len(sys.argv) > 3 else 14
-B, Hq, Hkv, S, D = 4, 32, 8, 4096, 128
+B, Hq, Hkv, S, D = (int(x) for x in os.environ.get("AULE_TRACE_SHAPE", "4,32,8,4096,128").split(","))   # config B: 4,32,32,2048,64
 g = torch.Generator(device="cuda").manual_seed(1)
 q = torch.randn(B, Hq, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
 k = torch.randn(B, Hkv, S, D, device="cuda", dtype=torch.bfloat16, generator=g)
