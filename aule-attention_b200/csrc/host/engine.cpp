@@ -160,6 +160,12 @@ std::string Engine::load_device(int ordinal) {
             e = check(drv_.cuFuncSetAttribute(d.bwd_fused_sm100[t], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                               (int)aule_kp::BwdFCfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd fused d128)");
     }
+    for (int t = 1; t < 3 && e.empty(); ++t) {
+        e = get(&d.bwd_fused2_sm100[t], std::string("aule_bwd_fused2_sm100_") + kDtypeSuffix[t] + "_d128");
+        if (e.empty())
+            e = check(drv_.cuFuncSetAttribute(d.bwd_fused2_sm100[t], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                              (int)aule_kp::BwdF2Cfg<128>::SMEM_BYTES), "cuFuncSetAttribute(smem bwd fused2 d128)");
+    }
     // tuning builds only: optional symbols
     for (int dd = 0; dd < 2; ++dd) {
         for (int v = 0; v < 16; ++v) {
@@ -283,7 +289,7 @@ std::string Engine::launch(Device& d, CUfunction fn, const char* name, unsigned 
 }
 
 std::string Engine::make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, uint64_t bh, uint64_t S, uint32_t D,
-                              bool mn_major_f32) const {
+                              bool mn_major_f32, uint32_t box_rows) const {
     // [bh, S, D] row-major viewed as a 3-D tensor (D innermost); box = 128 bytes x 128 rows x 1 (64 16-bit or 32 fp32
     // elements) with the 128-byte swizzle the UMMA descriptors in attn_fwd_sm100.cu expect. Out-of-range rows / columns
     // read as 0 and are clipped on store, which is how ragged Sq/Sk tails and padded head dims are handled.
@@ -292,7 +298,7 @@ std::string Engine::make_tmap(CUtensorMap* m, int32_t dtype, CUdeviceptr base, u
     const cuuint64_t es = f32 ? 4 : 2;
     cuuint64_t dims[3] = {D, S, bh};
     cuuint64_t strides[2] = {(cuuint64_t)D * es, (cuuint64_t)S * D * es};
-    cuuint32_t box[3] = {f32 ? 32u : 64u, 128, 1};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = drv_.cuTensorMapEncodeTiled(
         m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
@@ -483,7 +489,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             bp.win_right = causal ? 0u : (window > 0 ? (uint32_t)window / 2 : aule_kp::kWinInf);
             bp.win_left = window > 0 ? (causal ? (uint32_t)window - 1 : (uint32_t)window / 2) : aule_kp::kWinInf;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
-            bp.order = bwd_serial_ | (bwd_legacy_poll_ ? 4 : 0) | (bwd_single_s_ ? 8 : 0);
+            bp.order = bwd_serial_ | (bwd_legacy_poll_ ? 4 : 0) | (bwd_single_s_ ? 8 : 0) | (bwd_consumer_fence_ ? 16 : 0);
             // dK/dV CTA order: all units at once.  Launching the KV-block CTAs of a few (batch, kv-head) units together
             // (Q/dO L2-resident, BwdParams::units_per_run = ceil(SMs / KV blocks)) measured SLOWER: 1.36 vs 1.21 ms on
             // config C/2 (gpurun s21) -- the heavy CTAs of later runs start late and the tail grows.
@@ -493,7 +499,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             const uint64_t ctas = (uint64_t)((s.Sk + 127) / 128) * s.Hkv * s.B;
             const uint64_t ctas_dq = (uint64_t)((s.Sq + 127) / 128) * s.Hq * s.B;
             if (e.empty() && (ctas > 0x7fffffffull || ctas_dq > 0x7fffffffull)) e = "problem too large (backward grid exceeds 2^31 CTAs)";
-            if (e.empty() && bwd_fused_ && s.D == 128 && bwd_order_ == 0 && window < 0) {
+            if (e.empty() && (bwd_fused_ || bwd_fused2_) && s.D == 128 && bwd_order_ == 0 && window < 0) {
                 // Fused backward (attn_bwd_fused_sm100.cu): dK / dV as below, dQ reduced into an fp32 accumulator that is
                 // zeroed here and converted (x scale) afterwards.
                 const size_t n = (size_t)s.B * s.Hq * s.Sq * s.D;
@@ -504,7 +510,18 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
                 // CTA runs: the fp32 dQ rows a run reduces into (units x group x Sq x D x 4 bytes) should stay L2-resident
                 // while the run lasts, and the last run should be large enough that its heaviest CTAs do not make a tail.
                 bp.units_per_run = bwd_units_per_run_ ? (uint32_t)bwd_units_per_run_ : 8u;
-                if (e.empty()) {
+                if (e.empty() && bwd_fused2_) {
+                    // 64-query half steps: Q / dO travel in [64 rows][64 columns] boxes
+                    CUtensorMap tmQh, tmdOh;
+                    e = make_tmap(&tmQh, dtype, q, (uint64_t)s.B * s.Hq, s.Sq, s.D, false, 64);
+                    if (e.empty()) e = make_tmap(&tmdOh, dtype, d_o, (uint64_t)s.B * s.Hq, s.Sq, s.D, false, 64);
+                    if (e.empty()) {
+                        void* params[] = {&tmQh, &tmK, &tmV, &tmdOh, &tmdK, &tmdV, &bp};
+                        snprintf(name, sizeof(name), "aule_bwd_fused2_sm100_%s_d128", kDtypeSuffix[dtype]);
+                        e = launch(d, d.bwd_fused2_sm100[dtype], name, (unsigned)ctas, 1, 1, (unsigned)aule_kp::BwdF2Cfg<128>::THREADS,
+                                   aule_kp::BwdF2Cfg<128>::SMEM_BYTES, stream, params);
+                    }
+                } else if (e.empty()) {
                     void* params[] = {&tmQ, &tmK, &tmV, &tmdO, &tmdK, &tmdV, &bp};
                     snprintf(name, sizeof(name), "aule_bwd_fused_sm100_%s_d128", kDtypeSuffix[dtype]);
                     e = launch(d, d.bwd_fused_sm100[dtype], name, (unsigned)ctas, 1, 1, (unsigned)aule_kp::BwdFCfg<128>::THREADS,

@@ -9,4 +9,5 @@
 #endif
 #include "attn_bwd_sm100.cu"
 #include "attn_bwd_fused_sm100.cu"
+#include "attn_bwd_fused2_sm100.cu"
 #include "attn_paged_sm100.cu"

@@ -34,7 +34,7 @@ def call():
 
 
 serial = len(sys.argv) > 4 and sys.argv[4] == "serial"
-lib.aule_set_kernel_path((1 << 17) if which == "fused" else (((1 if which == "dkv" else 2) << 10) | ((1 << 12) if serial else 0)))
+lib.aule_set_kernel_path((1 << 26) if which == "fused2" else (1 << 17) if which == "fused" else (((1 if which == "dkv" else 2) << 10) | ((1 << 12) if serial else 0)))
 for _ in range(3):
     call()
 torch.cuda.synchronize()
@@ -65,6 +65,10 @@ if which == "fused":
              15: "iss: P half1 ok -> dV odd", 16: "iss: Q(s+2) ok -> S(s+2)",
              20: "cmp: wait dP", 21: "cmp: dP ok", 22: "cmp: dS math done", 23: "cmp: dS stored+fenced", 24: "cmp: S(s+1) ok",
              25: "cmp: P half0 published", 26: "cmp: dQ^T ok", 27: "cmp: drained"}
+if which == "fused2":
+    names = {10: "iss: wait dS", 11: "iss: dS ok -> dQ^T, dK", 12: "iss: dO(h+1) ok -> dP(h+1)", 13: "iss: P(h+1) ok -> dV", 16: "iss: Q(h+2) ok -> S(h+2)",
+             20: "cmp: wait dP", 21: "cmp: dP ok", 22: "cmp: dS math done, wait tile free", 23: "cmp: dS stored+fenced", 25: "cmp: P(h+1) published",
+             30: "drn: wait dQ^T", 26: "drn: dQ^T ok", 28: "cmp: dQ^T in regs, wait staging free", 29: "cmp: staging free", 27: "cmp: staged"}
 if which == "dq":
     names.update({10: "iss: step top (dQ(j-1) issued)", 16: "iss: sfree ok", 11: "iss: K(j+1) ok -> S(j+1)", 18: "iss: S(j+1) issued", 17: "iss: dpfree ok",
                   12: "iss: V(j+1) ok -> dP(j+1)", 19: "iss: dP(j+1) issued", 13: "iss: dS(j) ok -> dQ(j)"})

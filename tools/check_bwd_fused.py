@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "aule-attention_b200", "python"))
 from aule import cuda_flash, ffi  # noqa: E402
 
-FUSED = 1 << 17
+FUSED = (1 << int(os.environ.get("AULE_FUSED_BIT", "17"))) | int(os.environ.get("AULE_EXTRA_PATH", "0"))      # 17: first fused kernel, 26: 64-query half steps + TMA bulk reductions
 lib = ffi.ensure_init()
 
 
