@@ -489,7 +489,7 @@ std::string Engine::backward(int dev, CUstream stream, CUdeviceptr q, CUdevicept
             bp.win_right = causal ? 0u : (window > 0 ? (uint32_t)window / 2 : aule_kp::kWinInf);
             bp.win_left = window > 0 ? (causal ? (uint32_t)window - 1 : (uint32_t)window / 2) : aule_kp::kWinInf;
             bp.scale = scale; bp.scale_log2 = scale * 1.4426950408889634f; bp.causal = causal ? 1 : 0;
-            bp.order = bwd_serial_ | (bwd_legacy_poll_ ? 4 : 0) | (bwd_single_s_ ? 8 : 0) | (bwd_consumer_fence_ ? 16 : 0);
+            bp.order = bwd_serial_ | (bwd_legacy_poll_ ? 4 : 0) | (bwd_single_s_ ? 8 : 0) | (bwd_consumer_fence_ ? 16 : 0) | (bwd_fencer_ ? 32 : 0);
             // dK/dV CTA order: all units at once.  Launching the KV-block CTAs of a few (batch, kv-head) units together
             // (Q/dO L2-resident, BwdParams::units_per_run = ceil(SMs / KV blocks)) measured SLOWER: 1.36 vs 1.21 ms on
             // config C/2 (gpurun s21) -- the heavy CTAs of later runs start late and the tail grows.

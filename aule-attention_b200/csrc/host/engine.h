@@ -164,9 +164,10 @@ public:
     //   bit 24     backward dK/dV kernel: try_wait side polls in the issuer's load pump (the pre-round-2 behaviour; A/B)
     //   bit 25     backward dK/dV kernel, head_dim <= 64: one S^T buffer instead of two (the earlier behaviour; A/B)
     //   bit 27     backward, fused kernel of bit 26: proxy fence on the consumer side (A/B)
+    //   bit 28     backward, fused kernel of bit 26: proxy fence of the dS^T tile by a helper warp (A/B)
     //   bit 26     backward: fused kernel in 64-query half steps with TMA bulk reductions (attn_bwd_fused2_sm100.cu; D = 128)
     void set_kernel_path(int32_t p) {
-        bwd_fused_ = (p >> 17) & 1; bwd_units_per_run_ = (p >> 18) & 31; bwd_dq_v1_ = (p >> 23) & 1; bwd_legacy_poll_ = (p >> 24) & 1; bwd_single_s_ = (p >> 25) & 1; bwd_fused2_ = (p >> 26) & 1; bwd_consumer_fence_ = (p >> 27) & 1;
+        bwd_fused_ = (p >> 17) & 1; bwd_units_per_run_ = (p >> 18) & 31; bwd_dq_v1_ = (p >> 23) & 1; bwd_legacy_poll_ = (p >> 24) & 1; bwd_single_s_ = (p >> 25) & 1; bwd_fused2_ = (p >> 26) & 1; bwd_consumer_fence_ = (p >> 27) & 1; bwd_fencer_ = (p >> 28) & 1;
         pair_heads_enabled_ = !(p & 256); l2_runs_enabled_ = !(p & 512); cross_item_enabled_ = !(p & 32768); bwd_order_ = (p >> 10) & 3; bwd_serial_ = (p >> 12) & 3; fwd_v4_ = (p >> 14) & 1; bwd_two_streams_ = !(p & 65536); path_ = p & 255;
     }
     void set_trace_buffer(uint64_t dptr) { trace_ = dptr; }
@@ -203,6 +204,7 @@ private:
     int32_t bwd_single_s_ = 0;
     int32_t bwd_fused2_ = 0;
     int32_t bwd_consumer_fence_ = 0;
+    int32_t bwd_fencer_ = 0;
     int32_t bwd_units_per_run_ = 0;
     int32_t bwd_serial_ = 0;      // BwdParams::order. bit 0 (path bit 12), bring-up: the issuer waits for every MMA group
                                   // (tools/bwd_trace.py serial); bits 1-2 (path bits 13-14): polynomial-exp2 pairs of 4 (A/B)

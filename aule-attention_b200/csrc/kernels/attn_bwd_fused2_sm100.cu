@@ -22,8 +22,8 @@
 //     dQ_h^T -> registers -> staging tile [64 q][128 d] fp32 (lane = d: conflict-free) -> ONE bulk reduction of 32 KB
 //       into the fp32 accumulator [B,Hq,Sq,D] (64 consecutive query rows are contiguous there), issued by a reducer warp.
 //   P / dS warps per half step:  dS(h) | P(h+1);   drain warps: dQ^T(h);   tensor pipe:  dP^T(h+1) | dQ^T(h) dK(h) | dV(h+1) | S^T(h+2).
-//   Warps: 0-7 P / dS (thread = key row x 32 query columns), 8-15 drain (thread = d x 32 query columns), 16 = MMA + TMA-load
-//   issuer, 17 = reducer.  The drain is a latency chain of its own (wait, tcgen05.ld, 32 stores, proxy fence): on separate
+//   Warps: 0-15 P / dS (thread = key row x 16 query columns), 16-19 drain (thread = d x 64 query columns), 20 = MMA +
+//   TMA-load issuer, 21 = reducer.  The drain is a latency chain of its own (wait, tcgen05.ld, 32 stores, proxy fence): on separate
 //   warps it runs beside the P / dS chain instead of inside it (first version, 16 symmetric warps: 2630 cycles per half step).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -68,7 +68,8 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
     const uint32_t bar_stgfull0 = bar_stat0 + 16;       // compute -> reducer: staging tile h&1 written (8 arrivals) (+8)
     const uint32_t bar_stgfree0 = bar_stgfull0 + 16;    // reducer -> compute: the bulk reduction has read staging tile h&1 (+8)
     const uint32_t bar_dp1 = bar_stgfree0 + 16;         // dP^T(h) complete, odd h (dP^T is double-buffered: one barrier per buffer)
-    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 8 + 2 + 2 + 2 + 1) <= C::BAR_BYTES, "barrier area too small");
+    const uint32_t bar_dsw = bar_dp1 + 8;               // P / dS warps -> fencer warp: dS^T(h) written to SMEM (16 arrivals)
+    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 8 + 2 + 2 + 2 + 2) <= C::BAR_BYTES, "barrier area too small");
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
     float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [2][lse2 x128 | delta x128] per 128-query block step
     const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO, sdS = sb + C::OFF_DS;
@@ -80,14 +81,15 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
         for (int i = 0; i < NQ; ++i) { mbar_init(bar_qfull0 + 8 * i, 1); mbar_init(bar_qfree0 + 8 * i, 1); }
         for (int i = 0; i < NDO; ++i) { mbar_init(bar_dofull0 + 8 * i, 1); mbar_init(bar_dofree0 + 8 * i, 1); }
         mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_dq, 1); mbar_init(bar_dsfree, 1); mbar_init(bar_done, 1);
-        mbar_init(bar_p, 8); mbar_init(bar_ds, 8); mbar_init(bar_dqfree, 8);
+        mbar_init(bar_p, 16); mbar_init(bar_ds, (p.order & 32) ? 1 : 16); mbar_init(bar_dqfree, 4); mbar_init(bar_dsw, 16);
         mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4);
-        mbar_init(bar_stgfull0, 8); mbar_init(bar_stgfull0 + 8, 8);
+        mbar_init(bar_stgfull0, 4); mbar_init(bar_stgfull0 + 8, 4);
         mbar_init(bar_stgfree0, 1); mbar_init(bar_stgfree0 + 8, 1); mbar_init(bar_dp1, 1);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
-    if (warp == 16) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
+    constexpr uint32_t W_ISSUER = 20, W_REDUCER = 21, W_FENCER = 22;  // warps 0-15 P / dS, 16-19 drain
+    if (warp == W_ISSUER) tmem_alloc<512>(sb + C::OFF_TMEM_SLOT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -118,8 +120,12 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
     // CONSUMER thread (MMA issuer / reducer) after it has acquired the writers' mbarrier, instead of by every writer before
     // its arrive -- fence.proxy.async costs the writers ~400 cycles on their critical chain.
     const bool consumer_fence = (p.order & 16) != 0;
+    // BwdParams::order bit 5: a helper warp (22) executes that fence for the dS^T tile -- the 16 writer warps arrive on bar_dsw
+    // right after their stores, the helper acquires it, fences and arrives on bar_ds for the MMA issuer: the ~500-cycle fence
+    // then sits neither in the P / dS chain nor in the issuer's instruction stream.
+    const bool fencer = (p.order & 32) != 0;
 
-    if (warp == 16) {
+    if (warp == W_ISSUER) {
         // ===================================================== issuer
         if (elect_one() && nsteps > 0) {
             constexpr uint64_t HI_K = smem_desc_hi(16, 1024);                          // K-major SW128
@@ -135,6 +141,15 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             // (q-head, query block, half) of the next Q / dO load
             uint32_t ql = 0, ql_st = 0, ql_use = 0, ql_g = 0, ql_i = i_begin, ql_h = 0;
             uint32_t dl = 0, dl_st = 0, dl_use = 0, dl_g = 0, dl_i = i_begin, dl_h = 0;
+            // L2 prefetch cursors, PF tiles ahead of the loads: a Q / dO tile is requested only ~1.5 half steps before its MMA
+            // (ring depth), which does not cover a DRAM miss under this kernel's L2 traffic (trace: S^T(h+2) waited ~1500
+            // cycles for Q on every other half step)
+            constexpr uint32_t PF = 4;
+            uint32_t pq = 0, pq_g = 0, pq_i = i_begin, pq_h = 0, pd = 0, pd_g = 0, pd_i = i_begin, pd_h = 0;
+            for (uint32_t t = 0; t < PF; ++t) {
+                ++pq; if (++pq_h == 2) { pq_h = 0; if (++pq_i == nqb) { pq_i = i_begin; ++pq_g; } }
+                ++pd; if (++pd_h == 2) { pd_h = 0; if (++pd_i == nqb) { pd_i = i_begin; ++pd_g; } }
+            }
             auto pump = [&]() {
                 if (ql < nsteps && (ql_use == 0 || mbar_test(bar_qfree0 + 8 * ql_st, (ql_use - 1) & 1))) {
                     const uint32_t bar = bar_qfull0 + 8 * ql_st, dst = sQ0 + ql_st * C::Q_TILE_BYTES;
@@ -145,6 +160,12 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
                     ++ql;
                     if (++ql_h == 2) { ql_h = 0; if (++ql_i == nqb) { ql_i = i_begin; ++ql_g; } }
                     if (++ql_st == NQ) { ql_st = 0; ++ql_use; }
+                    if (pq < nsteps) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            tma_prefetch_3d(tmQ, c * 64, (int32_t)(pq_i * 128 + pq_h * 64), (int32_t)(b * p.Hq + hk * group + pq_g));
+                        ++pq; if (++pq_h == 2) { pq_h = 0; if (++pq_i == nqb) { pq_i = i_begin; ++pq_g; } }
+                    }
                 }
                 if (dl < nsteps && (dl_use == 0 || mbar_test(bar_dofree0 + 8 * dl_st, (dl_use - 1) & 1))) {
                     const uint32_t bar = bar_dofull0 + 8 * dl_st, dst = sdO0 + dl_st * C::Q_TILE_BYTES;
@@ -155,10 +176,11 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
                     ++dl;
                     if (++dl_h == 2) { dl_h = 0; if (++dl_i == nqb) { dl_i = i_begin; ++dl_g; } }
                     if (++dl_st == NDO) { dl_st = 0; ++dl_use; }
-                    if (dl < nsteps) {                                       // the tile after this one: warm it in L2 (2-stage ring)
+                    if (pd < nsteps) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
-                            tma_prefetch_3d(tmdO, c * 64, (int32_t)(dl_i * 128 + dl_h * 64), (int32_t)(b * p.Hq + hk * group + dl_g));
+                            tma_prefetch_3d(tmdO, c * 64, (int32_t)(pd_i * 128 + pd_h * 64), (int32_t)(b * p.Hq + hk * group + pd_g));
+                        ++pd; if (++pd_h == 2) { pd_h = 0; if (++pd_i == nqb) { pd_i = i_begin; ++pd_g; } }
                     }
                 }
             };
@@ -189,7 +211,7 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
                 const uint32_t sdO = sdO0 + (k % NDO) * C::Q_TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    mma_ts(tmem + COL_DV, tmem + COL_S + 32 * (kk >> 1) + 8 * (kk & 1), mk(HI_MNQ_HI, (HI_MNQ_LO | (sdO >> 4)) + kk * 128), ID_KMN, (k > 0 || kk > 0) ? 1u : 0u);
+                    mma_ts(tmem + COL_DV, tmem + COL_S + 16 * kk, mk(HI_MNQ_HI, (HI_MNQ_LO | (sdO >> 4)) + kk * 128), ID_KMN, (k > 0 || kk > 0) ? 1u : 0u);
                 mma_commit(bar_dofree0 + 8 * (k % NDO));
             };
             mbar_expect_tx(bar_kv, 2 * C::KV_TILE_BYTES);
@@ -260,7 +282,7 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             mma_commit(bar_done);
             wait(bar_done, 0);
         }
-    } else if (warp == 17) {
+    } else if (warp == W_REDUCER) {
         // ===================================================== reducer: one bulk reduction per half step
         if (elect_one() && nsteps > 0) {
             uint32_t g = 0, i = i_begin, half = 0;
@@ -283,48 +305,62 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             }
             tma_store_wait_read<0>();                                        // the CTA must outlive the reads of its shared memory
         }
-    } else if (warp >= 8) {
-        // ===================================================== drain warps 8-15: thread == (head-dim index d, 32 query columns)
+    } else if (warp == W_FENCER) {
+        if (fencer && elect_one()) {
+            for (uint32_t h = 0; h < nsteps; ++h) {
+                mbar_wait(bar_dsw, h & 1);
+                tc_fence_after();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_ds);
+            }
+        }
+    } else if (warp >= 16) {
+        // ===================================================== drain warps 16-19: thread == (head-dim index d, all 64 query columns)
         // dQ^T(h): TMEM -> registers -> staging tile [q][d] fp32 (consecutive lanes = consecutive d: conflict-free) -> the
-        // reducer's bulk reduction.  Their wait / load / store / fence chain runs beside the P / dS chain of warps 0-7, not in it.
-        const uint32_t dg = (warp >> 2) & 1;                         // query columns [32dg, 32dg+32) of the half step
+        // reducer's bulk reduction.  Their wait / load / store / fence chain runs beside the P / dS chain of warps 0-15, not in it.
         const uint32_t r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
-        const uint32_t tDQ = tmem + lane_addr + COL_DQ + 32 * dg;
-        Tracer tr(p.trace, 2, warp == 8 && lane == 0);
+        const uint32_t tDQ = tmem + lane_addr + COL_DQ;
+        Tracer tr(p.trace, 2, warp == 16 && lane == 0);
         for (uint32_t h = 0; h < nsteps; ++h) {
             tr.ev(30, h);
             mbar_wait(bar_dq, h & 1);
             tr.ev(26, h);
             tc_fence_after();
+            const uint32_t bsel = h & 1;
+            const uint32_t base = sStg0 + bsel * C::STG_BYTES + r * 4;
             uint32_t dq[32];
             tmem_ld32(tDQ, dq);
+            tmem_wait_ld();
+            tr.ev(28, h);
+            if (h >= 2) mbar_wait(bar_stgfree0 + 8 * bsel, ((h >> 1) - 1) & 1);   // the reduction of half step h-2 has read this tile
+            tr.ev(29, h);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + e * (D * 4)), "r"(dq[e]) : "memory");
+            tmem_ld32(tDQ + 32, dq);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_dqfree);
-            const uint32_t bsel = h & 1;
-            tr.ev(28, h);
-            if (h >= 2) mbar_wait(bar_stgfree0 + 8 * bsel, ((h >> 1) - 1) & 1);   // the reduction of half step h-2 has read this tile
-            tr.ev(29, h);
-            const uint32_t base = sStg0 + bsel * C::STG_BYTES + (32 * dg) * (D * 4) + r * 4;
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + e * (D * 4)), "r"(dq[e]) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (32 + e) * (D * 4)), "r"(dq[e]) : "memory");
             if (!consumer_fence) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_stgfull0 + 8 * bsel);
             tr.ev(27, h);
         }
     } else {
-        // ===================================================== P / dS warps 0-7: thread == (key row, 32 query columns)
-        const uint32_t qg = warp >> 2;                               // query columns [32qg, 32qg+32) of the half step
+        // ===================================================== P / dS warps 0-15: thread == (key row, 16 query columns)
+        const uint32_t qg = warp >> 2;                               // query columns [16qg, 16qg+16) of the half step
         const uint32_t r = (warp & 3) * 32 + lane;                   // TMEM lane == key row of S^T / dP^T
         const uint32_t lane_addr = ((warp & 3) * 32) << 16;
         const uint32_t key = key0 + r;
         const bool key_ok = key < p.Sk;
-        const uint32_t tS = tmem + lane_addr + COL_S + 32 * qg, tDP = tmem + lane_addr + COL_DP + 32 * qg;
-        const uint32_t ds_row = sdS + r * 128;                       // this thread's 64 bytes: 16-byte units (4qg + u) ^ (r&7)
+        const uint32_t tS = tmem + lane_addr + COL_S + 16 * qg, tDP = tmem + lane_addr + COL_DP + 16 * qg;
+        const uint32_t ds_row = sdS + r * 128;                       // this thread's 32 bytes: 16-byte units (2qg + u) ^ (r&7)
         // ---- column statistics (LSE, Delta of the 128 queries of a block step m = h >> 1): warps 0-3 publish them ahead
         const uint32_t t128 = threadIdx.x;                           // < 128 for the publishers
         float lse_n = 0.f, delta_n = 0.f;
@@ -350,7 +386,7 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             if (nblocks > 2) fetch_stats();                          // block step 2, published during half step 2
         }
         const float2 cc = make_float2(p.scale_log2, p.scale_log2);
-        float pv[32];                                                // P^T of the half step whose dS^T comes next (fp32)
+        float pv[16];                                                // P^T of the half step whose dS^T comes next (fp32)
         uint32_t i_p = i_begin;                                      // query block of the next P phase
         Tracer tr(p.trace, 1, warp == 0 && lane == 0);
         // P phase of half step k
@@ -358,25 +394,25 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             const uint32_t m = k >> 1, half = k & 1;
             if (half == 0) mbar_wait(bar_stat0 + 8 * (m & 1), (m >> 1) & 1);    // statistics of block step m are visible
             const uint32_t qrow0 = i_p * 128 + 64 * half;            // first query of the half step
-            const uint32_t q0 = qrow0 + 32 * qg;                     // first query of this thread's columns
+            const uint32_t q0 = qrow0 + 16 * qg;                     // first query of this thread's columns
             const bool diag = p.causal && (qrow0 < key0 + 128);
             const bool masked = diag || !key_ok || key0 + 128 > p.Sk || qrow0 + 64 > p.Sq;
-            uint32_t alive = 0xffffffffu;
+            uint32_t alive = 0xffffu;
             if (masked) {
                 const int64_t first = diag ? (int64_t)key - (int64_t)q0 : 0, last = (int64_t)p.Sq - 1 - (int64_t)q0;
-                const uint32_t lo_m = first <= 0 ? 0xffffffffu : (first > 31 ? 0u : (0xffffffffu << (int)first));
-                const uint32_t hi_m = last >= 31 ? 0xffffffffu : (last < 0 ? 0u : (0xffffffffu >> (31 - (int)last)));
+                const uint32_t lo_m = first <= 0 ? 0xffffu : (first > 15 ? 0u : ((0xffffu << (int)first) & 0xffffu));
+                const uint32_t hi_m = last >= 15 ? 0xffffu : (last < 0 ? 0u : (0xffffu >> (15 - (int)last)));
                 alive = key_ok ? (lo_m & hi_m) : 0u;
             }
             if (half == 1) { if (++i_p == nqb) i_p = i_begin; }
-            const float* sc = stat + (m & 1) * 256 + 64 * half + 32 * qg;        // this thread's 32 lse2
+            const float* sc = stat + (m & 1) * 256 + 64 * half + 16 * qg;        // this thread's 16 lse2
             mbar_wait(bar_s, k & 1);
             tc_fence_after();
-            uint32_t sreg[32];
-            tmem_ld32(tS, sreg);
+            uint32_t sreg[16];
+            tmem_ld16(tS, sreg);
             tmem_wait_ld();
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
+            for (int e4 = 0; e4 < 4; ++e4) {
                 const float4 l4 = *reinterpret_cast<const float4*>(sc + 4 * e4);       // broadcast
                 const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sreg[4 * e4]), __uint_as_float(sreg[4 * e4 + 1])), cc, make_float2(-l4.x, -l4.y));
                 const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sreg[4 * e4 + 2]), __uint_as_float(sreg[4 * e4 + 3])), cc, make_float2(-l4.z, -l4.w));
@@ -387,12 +423,12 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             }
             if (masked) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) pv[e] = (alive & (1u << e)) ? pv[e] : 0.f;
+                for (int e = 0; e < 16; ++e) pv[e] = (alive & (1u << e)) ? pv[e] : 0.f;
             }
-            uint32_t pk[16];
+            uint32_t pk[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) pk[e] = pack2<BF16>(pv[2 * e], pv[2 * e + 1]);
-            tmem_st16(tS, pk);                                       // packed P^T over the first 16 of this thread's 32 columns
+            for (int e = 0; e < 8; ++e) pk[e] = pack2<BF16>(pv[2 * e], pv[2 * e + 1]);
+            tmem_st8(tS, pk);                                        // packed P^T over the first 8 of this thread's 16 columns
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -407,12 +443,12 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             tr.ev(21, h);
             tc_fence_after();
             {
-                const float* sd = stat + (m & 1) * 256 + 128 + 64 * half + 32 * qg;       // this thread's 32 deltas
-                uint32_t dp[32], pk[16];
-                tmem_ld32(tDP + 64 * half, dp);
+                const float* sd = stat + (m & 1) * 256 + 128 + 64 * half + 16 * qg;       // this thread's 16 deltas
+                uint32_t dp[16], pk[8];
+                tmem_ld16(tDP + 64 * half, dp);
                 tmem_wait_ld();
 #pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
+                for (int e4 = 0; e4 < 4; ++e4) {
                     const float4 d4 = *reinterpret_cast<const float4*>(sd + 4 * e4);  // broadcast
                     const float2 a0 = __fmul2_rn(make_float2(pv[4 * e4], pv[4 * e4 + 1]),
                                                  __fadd2_rn(make_float2(__uint_as_float(dp[4 * e4]), __uint_as_float(dp[4 * e4 + 1])), make_float2(-d4.x, -d4.y)));
@@ -424,14 +460,14 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
                 tr.ev(22, h);
                 if (h > 0) mbar_wait(bar_dsfree, (h - 1) & 1);       // dQ^T(h-1) and dK(h-1) have read the tile
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t a = ds_row + (((4 * qg + u) ^ (r & 7)) << 4);
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t a = ds_row + (((2 * qg + u) ^ (r & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
                 }
-                if (!consumer_fence) fence_proxy_async_smem();
+                if (!consumer_fence && !fencer) fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_ds);
+                if (lane == 0) mbar_arrive(fencer ? bar_dsw : bar_ds);
                 // dQ^T(h-1) / dK(h-1) complete means every warp finished dS(h-1): when h is even that was the last reader of
                 // the statistics of block step m-1, whose buffer now takes block step m+1
                 if (half == 0 && h >= 2 && warp < 4 && m + 1 < nblocks) {
@@ -492,14 +528,14 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) tmem_dealloc<512>(tmem);
+    if (warp == W_ISSUER) tmem_dealloc<512>(tmem);
     if (threadIdx.x == 0) tma_store_wait_read<0>();                  // the CTA only has to outlive the reads of its shared memory
 }
 
 }  // namespace bwd100f2
 
 #define AULE_BWD100_FUSED2(NAME, BF)                                                                     \
-    extern "C" __global__ void __launch_bounds__(576, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
+    extern "C" __global__ void __launch_bounds__(736, 1) NAME(const __grid_constant__ CUtensorMap tmQ,    \
                                                               const __grid_constant__ CUtensorMap tmK,    \
                                                               const __grid_constant__ CUtensorMap tmV,    \
                                                               const __grid_constant__ CUtensorMap tmdO,   \

@@ -217,7 +217,7 @@ struct BwdFCfg {
 template <int D>
 struct BwdF2Cfg {
     static_assert(D == 128, "the fused backward is written for head_dim 128");
-    static constexpr int THREADS = 576;                         // 16 compute warps + issuer warp + reducer warp
+    static constexpr int THREADS = 736;                         // 16 P / dS warps + 4 drain warps + issuer, reducer, fence-helper warps
     static constexpr int NQ = 3, NDO = 2;
     static constexpr int QROWS = 64;                            // queries per half step
     static constexpr uint32_t KV_CHUNK_BYTES = 128 * 128;       // [128 keys][128 B]

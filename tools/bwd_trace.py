@@ -34,7 +34,7 @@ def call():
 
 
 serial = len(sys.argv) > 4 and sys.argv[4] == "serial"
-lib.aule_set_kernel_path((1 << 26) if which == "fused2" else (1 << 17) if which == "fused" else (((1 if which == "dkv" else 2) << 10) | ((1 << 12) if serial else 0)))
+lib.aule_set_kernel_path(((1 << 26) | int(os.environ.get("AULE_EXTRA_PATH", "0"))) if which == "fused2" else (1 << 17) if which == "fused" else (((1 if which == "dkv" else 2) << 10) | ((1 << 12) if serial else 0)))
 for _ in range(3):
     call()
 torch.cuda.synchronize()
