@@ -284,6 +284,46 @@ def test_fused_backward_kernel_vs_oracle(aule, B, Hq, Hkv, Sq, Sk, causal, dtype
         assert orc.rel_err_to_scale(g_.float().cpu().numpy(), e_) <= BF16_TOL
 
 
+@pytest.mark.parametrize("extra", [0, 1 << 28])
+@pytest.mark.parametrize("B,Hq,Hkv,Sq,Sk,causal,dtype", [
+    (1, 2, 1, 256, 256, True, "bf16"), (2, 4, 2, 1000, 1000, True, "f16"), (1, 2, 1, 300, 520, False, "bf16"), (1, 2, 2, 200, 200, True, "bf16"),
+    (1, 8, 2, 2048, 2048, True, "bf16")])
+def test_fused2_backward_kernel_vs_oracle(aule, B, Hq, Hkv, Sq, Sk, causal, dtype, extra):
+    """aule_set_kernel_path bit 26 (experimental, opt-in): the fused backward in 64-query half steps whose dQ partials leave
+    through TMA bulk reductions (attn_bwd_fused2_sm100.cu); bit 28 adds the fence-helper warp.  dK is bit-identical to the
+    two-kernel backward (same operands, same order); dV accumulates in 64-query steps and dQ through fp32 reductions, so both
+    are held to the bf16 bar against the fp64 oracle, like the reference's own atomics (triton_flash.py:335-347)."""
+    import torch
+    from aule import cuda_flash, ffi
+    lib = ffi.ensure_init()
+    td = {"bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    code = {"bf16": ffi.DTYPE_BF16, "f16": ffi.DTYPE_F16}[dtype]
+    q, k, v = ref_inputs(B, Hq, Sq, 128, Hkv=Hkv, Sk=Sk)
+    tq, tk, tv = (torch.from_numpy(np.ascontiguousarray(x)).cuda().to(td) for x in (q, k, v))
+    o, lse = cuda_flash.forward_with_lse(tq, tk, tv, causal=causal)
+    do = torch.randn(o.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).to(td)
+    fused2 = (1 << 26) | extra
+    res = {}
+    try:
+        for path in (0, fused2):
+            dq, dk, dv = (torch.full_like(t, float("nan")) for t in (tq, tk, tv))
+            lib.aule_set_kernel_path(path)
+            rc = lib.aule_attention_backward_dptr(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                                  dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, Hq, Hkv, Sq, Sk, 128, code, 0.0,
+                                                  1 if causal else 0, 0, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, ffi.last_error()
+            torch.cuda.synchronize()
+            res[path] = (dq, dk, dv, lib.aule_last_kernel().decode())
+    finally:
+        lib.aule_set_kernel_path(0)
+    assert res[0][3].startswith("aule_bwd_dq_sm100") and res[fused2][3].startswith("aule_bwd_dq_convert"), (res[0][3], res[fused2][3])
+    assert torch.equal(res[0][1], res[fused2][1])
+    edq, edk, edv, _, _ = orc.attention_bwd_ref(*(t.float().cpu().numpy() for t in (tq, tk, tv, do)), causal=causal)
+    for g_, e_ in zip(res[fused2][:3], (edq, edk, edv)):
+        assert bool(torch.isfinite(g_).all())
+        assert orc.rel_err_to_scale(g_.float().cpu().numpy(), e_) <= BF16_TOL
+
+
 # ------------------------------------------------------------------ RoPE
 @pytest.mark.parametrize("case", ["rope_gqa_1x4x64x64", "rope_mha_1x2x48x128"])
 def test_rope_vs_reference_golden(aule, golden_r2, case):
