@@ -68,13 +68,13 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
     const uint32_t bar_dp = bar_s + 8;                  // dP^T(h) complete (commit)
     const uint32_t bar_dq = bar_dp + 8;                 // dQ^T(h) complete (commit)
     const uint32_t bar_dsfree = bar_dq + 8;             // dQ^T(h) and dK(h) complete (commit): the dS^T tile may be rewritten
-    const uint32_t bar_p = bar_dsfree + 8;              // compute -> issuer: P^T(h) in TMEM (8 arrivals)
-    const uint32_t bar_ds = bar_p + 8;                  // compute -> issuer: dS^T(h) in SMEM, dP^T(h) in registers (8)
-    const uint32_t bar_dqfree = bar_ds + 8;             // compute -> issuer: dQ^T(h) in registers (8)
+    const uint32_t bar_p = bar_dsfree + 8;              // P / dS warps -> issuer: P^T(h) in TMEM (16 arrivals)
+    const uint32_t bar_ds = bar_p + 8;                  // -> issuer: dS^T(h) in SMEM, dP^T(h) in registers (16 P / dS warps, or 1: the fence helper)
+    const uint32_t bar_dqfree = bar_ds + 8;             // drain warps -> issuer: dQ^T(h) in registers (4 arrivals)
     const uint32_t bar_done = bar_dqfree + 8;           // every MMA complete (commit)
     const uint32_t bar_stat0 = bar_done + 8;            // publishers -> everyone: statistics of block step m in buffer m&1 (4 arrivals) (+8)
-    const uint32_t bar_stgfull0 = bar_stat0 + 16;       // compute -> reducer: staging tile h&1 written (8 arrivals) (+8)
-    const uint32_t bar_stgfree0 = bar_stgfull0 + 16;    // reducer -> compute: the bulk reduction has read staging tile h&1 (+8)
+    const uint32_t bar_stgfull0 = bar_stat0 + 16;       // drain warps -> reducer: staging tile h&1 written (4 arrivals) (+8)
+    const uint32_t bar_stgfree0 = bar_stgfull0 + 16;    // reducer -> drain warps: the bulk reductions have read staging tile h&1 (+8)
     const uint32_t bar_dp1 = bar_stgfree0 + 16;         // dP^T(h) complete, odd h (dP^T is double-buffered: one barrier per buffer)
     const uint32_t bar_dsw = bar_dp1 + 8;               // P / dS warps -> fencer warp: dS^T(h) written to SMEM (16 arrivals)
     static_assert(8 * (1 + 2 * NQ + 2 * NDO + 8 + 2 + 2 + 2 + 2) <= C::BAR_BYTES, "barrier area too small");
@@ -294,12 +294,12 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             wait(bar_done, 0);
         }
     } else if (warp == W_REDUCER) {
-        // ===================================================== reducer: one bulk reduction per half step
+        // ===================================================== reducer: the bulk reductions of a half step
         if (elect_one() && nsteps > 0) {
             uint32_t g = 0, i = i_begin, half = 0;
             for (uint32_t h = 0; h < nsteps; ++h) {
                 const uint32_t bsel = h & 1;
-                mbar_wait(bar_stgfull0 + 8 * bsel, (h >> 1) & 1);            // all 8 drain warps stored (and proxy-fenced) their part
+                mbar_wait(bar_stgfull0 + 8 * bsel, (h >> 1) & 1);            // the 4 drain warps stored (and proxy-fenced) their part
                 if (consumer_fence) fence_proxy_async_smem();
                 const uint32_t q0 = i * 128 + half * 64;
                 const uint32_t rows = q0 < p.Sq ? min(64u, p.Sq - q0) : 0u;
