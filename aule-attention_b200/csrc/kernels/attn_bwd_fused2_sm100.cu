@@ -303,9 +303,10 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
                 if (consumer_fence) fence_proxy_async_smem();
                 const uint32_t q0 = i * 128 + half * 64;
                 const uint32_t rows = q0 < p.Sq ? min(64u, p.Sq - q0) : 0u;
-                // The tile leaves in PIECE-row pieces, each a bulk group of its own, with at most two pieces in flight: the SM's
-                // TMA unit works its queue in order, and a Q / dO tile load queued behind one 32 KB reduction (~1400 cycles at
-                // 23-25 B/clk) arrived 1500-3000 cycles late (profiles/r2_s2_fused2_tma_reduce_trace.txt).
+                // The tile leaves in PIECE-row pieces, each a bulk group of its own, with at most two pieces in flight, so that a
+                // Q / dO tile load never queues behind one 32 KB reduction (~1400 cycles at 23-25 B/clk) in the SM's TMA unit.
+                // (Tile loads arrive 1500-3000 cycles late on every other half step -- profiles/r2_s2_fused2_tma_reduce_trace.txt;
+                // the pieces did not change that, so the queueing is not only here.  Kept: it costs nothing measurable.)
                 constexpr uint32_t PIECE = 8;                                // query rows per bulk reduction (4 KB)
                 float* dst = p.dq_acc + (((size_t)b * p.Hq + hk * group + g) * p.Sq + q0) * D;
                 for (uint32_t r0 = 0; r0 < rows; r0 += PIECE) {
