@@ -504,10 +504,14 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
     const uint32_t bar_done = bar_ds + 8;               // every MMA complete (commit)
     const uint32_t bar_pb = bar_done + 24;              // compute -> issuer: second half of P^T(i) (bar_p announces the first half)
     const uint32_t bar_s1 = bar_done + 32;              // S^T(i) complete, odd steps (D = 64: second S^T buffer, one barrier per buffer)
+    const uint32_t bar_p1 = bar_done + 40;              // bar_p / bar_pb of the second buffer: with S^T(i+1) available early a fast
+    const uint32_t bar_pb1 = bar_done + 48;             //   warp reaches step i+1 before a slow one has published P^T(i); on shared
+                                                        //   barriers those arrivals would complete step i's phase without the slow
+                                                        //   warp and dV(i) would read a P^T that is not there (tools/bwd_protocol_sim.py)
     const uint32_t bar_stat0 = bar_done + 8;            // publishers -> everyone: statistics of step s are in buffer s&1 (4 arrivals);
                                                         // one barrier per buffer, so a waiter can never be lapped (the next
                                                         // completion of ITS barrier needs its own dS^T arrival two steps on)
-    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 9) <= C::BAR_BYTES, "barrier area too small");
+    static_assert(8 * (1 + 2 * NQ + 2 * NDO + 11) <= C::BAR_BYTES, "barrier area too small");
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_SLOT);
     float* stat = reinterpret_cast<float*>(smem + C::OFF_STAT);      // [3][lse2 x128 | delta x128]
     const uint32_t sK = sb + C::OFF_K, sV = sb + C::OFF_V, sQ0 = sb + C::OFF_Q, sdO0 = sb + C::OFF_DO;
@@ -518,7 +522,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
         for (int i = 0; i < NQ; ++i) { mbar_init(bar_qfull0 + 8 * i, 1); mbar_init(bar_qfree0 + 8 * i, 1); }
         for (int i = 0; i < NDO; ++i) { mbar_init(bar_dofull0 + 8 * i, 1); mbar_init(bar_dofree0 + 8 * i, 1); }
         mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_p, 16); mbar_init(bar_ds, 16); mbar_init(bar_done, 1);
-        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4); mbar_init(bar_pb, 16); mbar_init(bar_s1, 1);
+        mbar_init(bar_stat0, 4); mbar_init(bar_stat0 + 8, 4); mbar_init(bar_pb, 16); mbar_init(bar_s1, 1); mbar_init(bar_p1, 16); mbar_init(bar_pb1, 16);
         fence_mbar_init();
         tma_prefetch_desc(tmQ); tma_prefetch_desc(tmK); tma_prefetch_desc(tmV); tma_prefetch_desc(tmdO);
     }
@@ -645,14 +649,16 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                 {
                     const uint32_t sdO = sdO0 + ds_ * C::TILE_BYTES;
                     tr.ev(17, step);
-                    wait(bar_p, step & 1);                                   // first halves of P^T(step) in TMEM
+                    const bool odd_b = two_s && (step & 1);
+                    const uint32_t p_par = two_s ? ((step >> 1) & 1) : (step & 1);
+                    wait(odd_b ? bar_p1 : bar_p, p_par);                     // first halves of P^T(step) in TMEM
                     tr.ev(18, step);
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < 8; kk += 2)
                         mma_ts(tmem + COL_DV, tmem + colS + 32 * (kk >> 1) + 8 * (kk & 1),
                                mk(HI_MN_HI, (HI_MN_LO | (sdO >> 4)) + kk * 128), ID_KMN, (step > 0 || kk > 0) ? 1u : 0u);
-                    wait(bar_pb, step & 1);                                  // second halves
+                    wait(odd_b ? bar_pb1 : bar_pb, p_par);                   // second halves
                     tc_fence_after();
 #pragma unroll
                     for (int kk = 1; kk < 8; kk += 2)
@@ -798,7 +804,7 @@ __device__ __forceinline__ void bwd_dkv_t_body(const CUtensorMap* tmQ, const CUt
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(half ? bar_pb : bar_p);
+                    if (lane == 0) mbar_arrive(half ? (odd_buf ? bar_pb1 : bar_pb) : (odd_buf ? bar_p1 : bar_p));
                     if (half == 0) tr.ev(28, step);
                 }
             }

@@ -183,7 +183,7 @@ struct BwdTCfg {
     static constexpr uint32_t OFF_DO = (2 + NQ) * TILE_BYTES;
     static constexpr uint32_t OFF_STAT = (2 + NQ + NDO) * TILE_BYTES;
     static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 256 * 4;   // two statistics buffers (published one step ahead)
-    static constexpr uint32_t BAR_BYTES = 160;
+    static constexpr uint32_t BAR_BYTES = 176;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
