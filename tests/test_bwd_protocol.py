@@ -38,6 +38,14 @@ def test_dkv_kernel_shared_s_barrier_is_caught():
     assert not any(sim.dkvt(two_s=True, seed=s, per_buffer_bar=False, slow_warp=300)[0] for s in SEEDS)
 
 
+@pytest.mark.parametrize("slow", [0, 300])
+def test_dq_kernel_protocol_is_clean(slow):
+    """dQ kernel v2: three issuer threads whose commits only cover their own MMAs."""
+    for seed in SEEDS:
+        ok, detail = sim.dq2(seed=seed, slow_warp=slow)
+        assert ok, detail
+
+
 @pytest.mark.parametrize("drain_delay,slow", [(0, 0), (400, 0), (0, 300)])
 def test_fused2_protocol_is_clean(drain_delay, slow):
     for seed in SEEDS:

@@ -12,6 +12,7 @@ many random schedules finish without a violated assertion or a deadlock.
 
 Models (each mirrors the barrier code of the kernel it names; the kernels' own comments carry the same rules):
   dkvt(two_s)          csrc/kernels/attn_bwd_sm100.cu  bwd_dkv_t_body: one or two S^T buffers (head_dim <= 64 has two)
+  dq2()                csrc/kernels/attn_bwd_sm100.cu  bwd_dq2_body: three issuer threads with separate commit scopes
   fused2(wait_dqfree)  csrc/kernels/attn_bwd_fused2_sm100.cu: 64-query half steps, separate drain warps and reducer;
                        wait_dqfree=False is the version that hung under ncu (the issuer overwrote dQ^T(h-1) before the
                        drain warps had read it and lapped them on bar_dq)
@@ -67,23 +68,25 @@ class Machine:
         self.rng = random.Random(seed)
         self.max_delay = max_delay
         self.pipe = []                           # in-order tensor pipe: [remaining, fn]
+        self.pipes = {}                          # further issuing threads: ops are ordered (and commits count) per thread only
         self.tma = []                            # independent loads: [remaining, fn]
         self.actors = []
 
-    def mma(self, fn):                           # tcgen05.mma group: executes in issue order
-        self.pipe.append([self.rng.randint(1, self.max_delay), fn])
+    def mma(self, fn, thread=None):              # tcgen05.mma group: executes in issue order (of its issuing thread)
+        (self.pipe if thread is None else self.pipes.setdefault(thread, [])).append([self.rng.randint(1, self.max_delay), fn])
 
-    def commit(self, bar):                       # tcgen05.commit: arrives once everything issued before it has executed
-        self.pipe.append([1, bar.arrive])
+    def commit(self, bar, thread=None):          # tcgen05.commit: arrives once everything this thread issued before has executed
+        (self.pipe if thread is None else self.pipes.setdefault(thread, [])).append([1, bar.arrive])
 
     def load(self, fn):
         self.tma.append([self.rng.randint(1, 3 * self.max_delay), fn])
 
     def tick(self):
-        if self.pipe:
-            self.pipe[0][0] -= 1
-            if self.pipe[0][0] <= 0:
-                self.pipe.pop(0)[1]()
+        for q in [self.pipe] + list(self.pipes.values()):
+            if q:
+                q[0][0] -= 1
+                if q[0][0] <= 0:
+                    q.pop(0)[1]()
         for t in list(self.tma):
             t[0] -= 1
             if t[0] <= 0:
@@ -110,7 +113,7 @@ class Machine:
                     continue
                 if r != "wait":
                     progressed = True
-            idle = 0 if (progressed or self.pipe or self.tma) else idle + 1
+            idle = 0 if (progressed or self.pipe or self.tma or any(self.pipes.values())) else idle + 1
             if idle > 2000:
                 return False, "deadlock: every actor waits and nothing is in flight"
         return False, "did not finish"
@@ -219,6 +222,112 @@ def dkvt(nsteps=24, two_s=True, W=4, NQ=3, NDO=2, seed=0, per_buffer_bar=True, p
             bar_ds.arrive()
 
     m.actors = [issuer()] + [warp(w) for w in range(W)]
+    try:
+        return m.run()
+    except Violation as e:
+        return False, str(e)
+
+
+# ------------------------------------------------------------------------------------------------ dQ kernel v2
+def dq2(n=24, W=4, NK=4, NV=2, seed=0, slow_warp=0):
+    """bwd_dq2_body: three issuer threads (S stream + K loads, dP stream + V loads, dQ stream), each with its own commit
+    scope, W compute warps (kernel: 16).  S, dP and dS have one buffer each; dQ accumulates."""
+    m = Machine(seed)
+    kfull, kfree = [Bar(1) for _ in range(NK)], [Bar(1) for _ in range(NK)]
+    vfull, vfree = [Bar(1) for _ in range(NV)], [Bar(1) for _ in range(NV)]
+    bar_q, bar_do, bar_s, bar_dp, bar_dsfree = Bar(W), Bar(1), Bar(1), Bar(1), Bar(1)
+    bar_sfree, bar_dpfree, bar_ds = Bar(W), Bar(W), Bar(W)
+    K, V = [Buf(f"K[{i}]") for i in range(NK)], [Buf(f"V[{i}]") for i in range(NV)]
+    S, DP, DS = Buf("S"), Buf("dP"), Buf("dS")
+
+    def s_stream():
+        st = {"kl": 0}
+
+        def pump():
+            kl = st["kl"]
+            if kl < n and (kl < NK or kfree[kl % NK].test(((kl // NK) - 1) & 1)):
+                m.load(lambda j=kl: (K[j % NK].write(("K", j), 2), kfull[j % NK].arrive()))      # read by S(j) and dQ(j)
+                st["kl"] += 1
+
+        def issue_s(j):
+            m.mma(lambda: (K[j % NK].read(("K", j)), S.write(("S", j), W)), "s")
+            m.commit(bar_s, "s")
+
+        for _ in range(NK):
+            pump()
+        yield from wait(bar_q, 0)
+        yield from wait(kfull[0], 0)
+        issue_s(0)
+        for j in range(n - 1):
+            pump()
+            yield from wait(bar_sfree, j & 1)
+            while not kfull[(j + 1) % NK].test(((j + 1) // NK) & 1):
+                pump()
+                yield "wait"
+            issue_s(j + 1)
+        while st["kl"] < n:
+            pump()
+            yield "wait"
+
+    def dp_stream():
+        st = {"vl": 0}
+
+        def pump():
+            vl = st["vl"]
+            if vl < n and (vl < NV or vfree[vl % NV].test(((vl // NV) - 1) & 1)):
+                m.load(lambda j=vl: (V[j % NV].write(("V", j), 1), vfull[j % NV].arrive()))
+                st["vl"] += 1
+
+        def issue_dp(j):
+            m.mma(lambda: (V[j % NV].read(("V", j)), DP.write(("dP", j), W)), "dp")
+            m.commit(bar_dp, "dp")
+            m.commit(vfree[j % NV], "dp")
+
+        m.load(bar_do.arrive)
+        for _ in range(NV):
+            pump()
+        yield from wait(bar_do, 0)
+        yield from wait(vfull[0], 0)
+        issue_dp(0)
+        for j in range(n - 1):
+            pump()
+            yield from wait(bar_dpfree, j & 1)
+            while not vfull[(j + 1) % NV].test(((j + 1) // NV) & 1):
+                pump()
+                yield "wait"
+            issue_dp(j + 1)
+
+    def dq_stream():
+        for j in range(n):
+            yield from wait(bar_ds, j & 1)
+            m.mma(lambda j=j: (DS.read(("dS", j)), K[j % NK].read(("K", j))), "dq")
+            m.commit(kfree[j % NK], "dq")
+            m.commit(bar_dsfree, "dq")
+
+    done_ds = [0] * n
+
+    def warp(w):
+        bar_q.arrive()
+        for j in range(n):
+            for _ in range(slow_warp if w == 0 else 0):
+                yield
+            yield from wait(bar_s, j & 1)
+            S.read(("S", j))
+            bar_sfree.arrive()
+            yield
+            yield from wait(bar_dp, j & 1)
+            DP.read(("dP", j))
+            bar_dpfree.arrive()
+            yield
+            if j > 0:
+                yield from wait(bar_dsfree, (j - 1) & 1)
+            done_ds[j] += 1
+            if done_ds[j] == 1:
+                DS.write(("dS", j), 1)
+            yield
+            bar_ds.arrive()
+
+    m.actors = [s_stream(), dp_stream(), dq_stream()] + [warp(w) for w in range(W)]
     try:
         return m.run()
     except Violation as e:
@@ -363,6 +472,7 @@ if __name__ == "__main__":
                      ("dkvt, two S^T buffers, one slow warp", lambda s: dkvt(two_s=True, seed=s, slow_warp=300)),
                      ("dkvt, two buffers, shared P^T barriers, slow warp", lambda s: dkvt(two_s=True, seed=s, per_buffer_pbar=False, slow_warp=300)),
                      ("dkvt, two buffers, shared S^T barrier, slow warp", lambda s: dkvt(two_s=True, seed=s, per_buffer_bar=False, slow_warp=300)),
+                     ("dq2 (three issuer threads)", lambda s: dq2(seed=s)), ("dq2, one slow warp", lambda s: dq2(seed=s, slow_warp=300)),
                      ("fused2, one slow P / dS warp", lambda s: fused2(seed=s, slow_warp=300)),
                      ("fused2", lambda s: fused2(seed=s)), ("fused2, slow drain", lambda s: fused2(seed=s, drain_delay=400)),
                      ("fused2 without the bar_dqfree wait, slow drain", lambda s: fused2(wait_dqfree=False, seed=s, drain_delay=400))):
