@@ -298,8 +298,8 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
         if (elect_one() && nsteps > 0) {
             uint32_t g = 0, i = i_begin, half = 0;
             for (uint32_t h = 0; h < nsteps; ++h) {
-                const uint32_t bsel = h & 1;
-                mbar_wait(bar_stgfull0 + 8 * bsel, (h >> 1) & 1);            // the 4 drain warps stored (and proxy-fenced) their part
+                const uint32_t bsel = (C::STG_BUFS == 2) ? (h & 1) : 0u;
+                mbar_wait(bar_stgfull0 + 8 * bsel, (C::STG_BUFS == 2) ? ((h >> 1) & 1) : (h & 1));            // the 4 drain warps stored (and proxy-fenced) their part
                 if (consumer_fence) fence_proxy_async_smem();
                 const uint32_t q0 = i * 128 + half * 64;
                 const uint32_t rows = q0 < p.Sq ? min(64u, p.Sq - q0) : 0u;
@@ -344,13 +344,17 @@ __device__ __forceinline__ void bwd_fused2_body(const CUtensorMap* tmQ, const CU
             mbar_wait(bar_dq, h & 1);
             tr.ev(26, h);
             tc_fence_after();
-            const uint32_t bsel = h & 1;
+            const uint32_t bsel = (C::STG_BUFS == 2) ? (h & 1) : 0u;
             const uint32_t base = sStg0 + bsel * C::STG_BYTES + r * 4;
             uint32_t dq[32];
             tmem_ld32(tDQ, dq);
             tmem_wait_ld();
             tr.ev(28, h);
-            if (h >= 2) mbar_wait(bar_stgfree0 + 8 * bsel, ((h >> 1) - 1) & 1);   // the reduction of half step h-2 has read this tile
+            if constexpr (C::STG_BUFS == 2) {
+                if (h >= 2) mbar_wait(bar_stgfree0 + 8 * bsel, ((h >> 1) - 1) & 1);   // the reduction of half step h-2 has read this tile
+            } else {
+                if (h >= 1) mbar_wait(bar_stgfree0, (h - 1) & 1);                     // one tile: the reduction of half step h-1 has read it
+            }
             tr.ev(29, h);
 #pragma unroll
             for (int e = 0; e < 32; ++e)

@@ -211,6 +211,12 @@ struct BwdFCfg {
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
+// (A/B at build time: -DAULE_F2_NQ=4 -DAULE_F2_NDO=3 -DAULE_F2_STG=1 trades the second staging tile for deeper Q / dO rings)
+#ifndef AULE_F2_NQ
+#define AULE_F2_NQ 3
+#define AULE_F2_NDO 2
+#define AULE_F2_STG 2
+#endif
 // Fused backward in 64-query half steps (attn_bwd_fused2_sm100.cu): the dQ partial of a half step is a [64 q][128 d] fp32
 // tile that is staged in shared memory and added into the global accumulator by ONE asynchronous TMA bulk reduction.
 // K_j | V_j | Q ring (3 x [64][128]) | dO ring (2) | dS^T tile [128 keys][64 q] | 2 staging tiles (32 KB each) | statistics | barriers.
@@ -218,7 +224,8 @@ template <int D>
 struct BwdF2Cfg {
     static_assert(D == 128, "the fused backward is written for head_dim 128");
     static constexpr int THREADS = 736;                         // 16 P / dS warps + 4 drain warps + issuer, reducer, fence-helper warps
-    static constexpr int NQ = 3, NDO = 2;
+    static constexpr int NQ = AULE_F2_NQ, NDO = AULE_F2_NDO;
+    static constexpr int STG_BUFS = AULE_F2_STG;                // fp32 staging tiles (32 KB each)
     static constexpr int QROWS = 64;                            // queries per half step
     static constexpr uint32_t KV_CHUNK_BYTES = 128 * 128;       // [128 keys][128 B]
     static constexpr uint32_t KV_TILE_BYTES = 2 * KV_CHUNK_BYTES;
@@ -231,9 +238,9 @@ struct BwdF2Cfg {
     static constexpr uint32_t OFF_DO = OFF_Q + NQ * Q_TILE_BYTES;
     static constexpr uint32_t OFF_DS = OFF_DO + NDO * Q_TILE_BYTES;
     static constexpr uint32_t OFF_STG = OFF_DS + DS_BYTES;
-    static constexpr uint32_t OFF_STAT = OFF_STG + 2 * STG_BYTES;
+    static constexpr uint32_t OFF_STAT = OFF_STG + STG_BUFS * STG_BYTES;
     static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 256 * 4;
-    static constexpr uint32_t BAR_BYTES = 224;
+    static constexpr uint32_t BAR_BYTES = 256;
     static constexpr uint32_t OFF_TMEM_SLOT = OFF_BAR + BAR_BYTES;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM_SLOT + 16;
     static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");

@@ -335,7 +335,7 @@ def dq2(n=24, W=4, NK=4, NV=2, seed=0, slow_warp=0):
 
 
 # ------------------------------------------------------------------------------------------------ fused backward, half steps
-def fused2(nsteps=24, wait_dqfree=True, W=4, WD=2, NQ=3, NDO=2, seed=0, drain_delay=0, slow_warp=0):
+def fused2(nsteps=24, wait_dqfree=True, W=4, WD=2, NQ=3, NDO=2, seed=0, drain_delay=0, slow_warp=0, stg_bufs=2):
     """bwd_fused2_body: W P / dS warps (kernel: 16), WD drain warps (kernel: 4), an issuer and a reducer.
     drain_delay > 0 makes the drain warps slow (what ncu's replay passes did)."""
     m = Machine(seed)
@@ -444,20 +444,24 @@ def fused2(nsteps=24, wait_dqfree=True, W=4, WD=2, NQ=3, NDO=2, seed=0, drain_de
             DQ.read(("dQ", h))
             yield
             bar_dqfree.arrive()
-            if h >= 2:
-                yield from wait(stgfree[h & 1], ((h >> 1) - 1) & 1)
+            b = (h & 1) if stg_bufs == 2 else 0
+            if stg_bufs == 2 and h >= 2:
+                yield from wait(stgfree[b], ((h >> 1) - 1) & 1)
+            if stg_bufs == 1 and h >= 1:
+                yield from wait(stgfree[0], (h - 1) & 1)
             done_stg[h] += 1
             if done_stg[h] == 1:
-                STG[h & 1].write(("stg", h), 1)
+                STG[b].write(("stg", h), 1)
             yield
-            stgfull[h & 1].arrive()
+            stgfull[b].arrive()
 
     def reducer():
         for h in range(nsteps):
-            yield from wait(stgfull[h & 1], (h >> 1) & 1)
-            STG[h & 1].read(("stg", h))
+            b = (h & 1) if stg_bufs == 2 else 0
+            yield from wait(stgfull[b], ((h >> 1) & 1) if stg_bufs == 2 else (h & 1))
+            STG[b].read(("stg", h))
             yield
-            stgfree[h & 1].arrive()
+            stgfree[b].arrive()
 
     m.actors = [issuer(), reducer()] + [pds_warp(w) for w in range(W)] + [drain_warp(w) for w in range(WD)]
     try:
